@@ -1,0 +1,222 @@
+/* kvhbm.h — C ABI of the B200-native KvVariable hot path (libkvhbm.so).
+ *
+ * This is the drop-in boundary: each entry point is what a TensorFlow 2.13
+ * DEVICE_GPU OpKernel for the TFPlus op of the same meaning calls on the op's
+ * CUDA stream (glue in tf_ops/, binding shown in INTEGRATION.md).  Plain
+ * pointers and sizes only; every `d_*` pointer is DEVICE memory on the table's
+ * GPU, everything else is host.  All functions return a kv_status (0 = OK);
+ * kv_last_error() gives the message of the calling thread's last failure.
+ * Work is enqueued on `stream` (a cudaStream_t passed as void*); functions that
+ * return a host scalar synchronise that stream and say so.
+ *
+ * Keys are int64, values fp32 (the reference also registers int32/uint64 keys
+ * and half values, kv_variable_ops.cc:127-156; those return KV_UNIMPLEMENTED).
+ * Two key values are reserved as slot sentinels: INT64_MIN and INT64_MIN+1.
+ *
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * KV_INTERNAL.
+ *
+ * Citations are file:line under /root/reference/tfplus/kv_variable/.
+ */
+#ifndef KVHBM_H_
+#define KVHBM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kv_table kv_table;         /* one KvVariable<int64,float> resource */
+typedef struct kv_workspace kv_workspace; /* scratch for dedup / routing kernels */
+typedef void* kv_stream;                  /* cudaStream_t */
+
+typedef enum {
+  KV_OK = 0,
+  KV_INVALID_ARGUMENT = 1,    /* errors::InvalidArgument */
+  KV_FAILED_PRECONDITION = 2, /* errors::FailedPrecondition (uninitialized var) */
+  KV_UNIMPLEMENTED = 3,
+  KV_RESOURCE_EXHAUSTED = 4,  /* out of HBM */
+  KV_INTERNAL = 5             /* CUDA error */
+} kv_status;
+
+/* kernels/kv_variable_interface.h ScatterUpdateOps */
+typedef enum {
+  KV_SCATTER_ASSIGN = 0, KV_SCATTER_ADD = 1, KV_SCATTER_SUB = 2,
+  KV_SCATTER_MUL = 3, KV_SCATTER_DIV = 4, KV_SCATTER_MIN = 5, KV_SCATTER_MAX = 6
+} kv_scatter_op;
+
+const char* kv_last_error(void);
+/* Number of kernel launches this library has issued in this process (bench
+ * bookkeeping: the `gpu_launches` claim is read from here, not guessed). */
+int64_t kv_launch_count(void);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* CreateKvVariableOp::Compute, kernels/kv_variable_ops.cc:58-116 ->
+ * KvVariable ctor kernels/kv_variable.h:92-114.  `capacity_hint` keys are
+ * pre-sized (0 = default); the table grows on demand.  Uses the current CUDA
+ * device. */
+int kv_create(int dim, int enter_threshold, int64_t capacity_hint, kv_table** out);
+/* DestroyKvVariableOp, kernels/kv_variable_ops.cc:295-323. */
+int kv_destroy(kv_table* t);
+int kv_dim(const kv_table* t);
+int kv_enter_threshold(const kv_table* t);
+/* Seed of the deterministic initializer that replaces std::rand()
+ * (kernels/kv_variable.h:889-898; DESIGN.md "initializer"). */
+int kv_set_seed(kv_table* t, uint64_t seed);
+/* Make room for `n_keys` more keys now, so that later calls never have to
+ * resize (needed before CUDA-graph capture). */
+int kv_reserve(kv_table* t, int64_t n_keys, kv_stream stream);
+/* InitKvVariableOp -> KvVariable::InitRandomValues, kernels/kv_variable.h:184-206:
+ * copies d_table[rows, dim]; only the first call takes effect. */
+int kv_set_init_table(kv_table* t, const float* d_table, int64_t rows, kv_stream stream);
+/* KvVariableIsInitializedOp, kernels/kv_variable_ops.cc:214-237. */
+int kv_is_initialized(const kv_table* t, int* out);
+int kv_init_table_rows(const kv_table* t, int64_t* rows);
+int kv_get_init_table(const kv_table* t, float* d_out, kv_stream stream);
+/* KvVariableSizeOp / KvVariableFrequencyOp / KvVariableShapeOp,
+ * kernels/kv_variable_ops.cc:239-293,159-186 -> kv_variable.h:139-182.
+ * size = keys not blacklisted with freq >= enter_threshold; map_size = all
+ * keys (shape[0]).  Synchronise `stream`. */
+int kv_size(kv_table* t, kv_stream stream, int64_t* out);
+int kv_sum_freq(kv_table* t, kv_stream stream, int64_t* out);
+int kv_map_size(kv_table* t, kv_stream stream, int64_t* out);
+
+/* ---- lookups ------------------------------------------------------------ */
+
+/* KvVariableGatherOrInsertOp / ...WithCountsOp, kernels/kv_variable_ops.cc:498-631
+ * -> KvVariable::FindOrInsert kernels/kv_variable.h:263-380.
+ * d_ids[n] int64, d_counts[n] int32 or NULL, d_out[n, dim].  `today` is
+ * time()/86400 truncated to 16 bits (kernels/utility.cc:38-40), injected. */
+int kv_gather_or_insert(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
+                        int64_t n, float* d_out, uint16_t today, kv_stream stream);
+/* KvVariableGatherOrZerosOp, kernels/kv_variable_ops.cc:348-429 ->
+ * KvVariable::FindOrZeros kernels/kv_variable.h:239-254. */
+int kv_gather_or_zeros(kv_table* t, const int64_t* d_ids, int64_t n, float* d_out,
+                       kv_stream stream);
+/* KvVariableInsertOp, kernels/kv_variable_ops.cc:703-747 ->
+ * KvVariable::InsertOrUpdate kernels/kv_variable.h:423-485.  d_filter_out /
+ * d_blacklist are uint8[n] masks or NULL.  Ids must be unique. */
+int kv_insert_or_update(kv_table* t, const int64_t* d_ids, const float* d_values,
+                        int64_t n, const uint8_t* d_filter_out,
+                        const uint8_t* d_blacklist, kv_stream stream);
+/* KvVariableScatterUpdateOP<op>, kernels/kv_variable_ops.cc:1097-1163 ->
+ * KvVariable::ScatterUpdate kernels/kv_variable.h:616-734.  Ids must be unique
+ * (TF dedups before the optimizer reaches this op). */
+int kv_scatter(kv_table* t, int op, const int64_t* d_ids, const float* d_updates,
+               int64_t n, kv_stream stream);
+/* KvVariable::GetCount / GetTimeStamp, kernels/kv_variable.h:503-561 (ops
+ * KvVariableGetCountV2 / KvVariableGetTimeStamp have no kernel in the OSS tree). */
+int kv_get_count(kv_table* t, const int64_t* d_ids, int64_t n, int32_t* d_out,
+                 kv_stream stream);
+int kv_get_timestamp(kv_table* t, const int64_t* d_ids, int64_t n, uint32_t* d_out,
+                     uint16_t today, kv_stream stream);
+
+/* ---- fused sparse optimizer applies -------------------------------------
+ * d_ids[n] must be unique (what TF's _deduplicate_indexed_slices hands the op).
+ * If d_n is non-NULL the number of valid ids is read from *d_n on the device
+ * (<= n), which lets unique -> segment_sum -> apply run without a host sync. */
+
+/* KvVariableSparseApplyAdagradOp, kernels/training_ops.cc:1372-1520. */
+int kv_apply_adagrad(kv_table* var, kv_table* accum, const int64_t* d_ids,
+                     const float* d_grad, int64_t n, const int32_t* d_n, float lr,
+                     int update_slots, uint16_t today, kv_stream stream);
+/* KvVariableGroupSparseApplyAdamV4Op, kernels/training_ops.cc:6980-7235.
+ * m_v_linear has dim 3*dim(var) = [m | v | linear]. */
+int kv_apply_group_adam_v4(kv_table* var, kv_table* m_v_linear, const int64_t* d_ids,
+                           const float* d_grad, int64_t n, const int32_t* d_n,
+                           float lr, float beta1_power, float beta2_power,
+                           float beta1, float beta2, float epsilon, float l1,
+                           float l2, float l21, uint16_t today, kv_stream stream);
+/* KvVariableSparseGroupSparseApplyFtrlOp<has_l2_shrinkage=true>,
+ * kernels/training_ops.cc:532-801. */
+int kv_apply_sparse_group_ftrl(kv_table* var, kv_table* accum, kv_table* linear,
+                               const int64_t* d_ids, const float* d_grad, int64_t n,
+                               const int32_t* d_n, float lr, float l1, float l2,
+                               float l21, float l2_shrinkage, float lr_power,
+                               uint16_t today, kv_stream stream);
+/* tfplus AdamOptimizer._tfplus_apply_sparse_shared, python/training/adam.py:93-163,
+ * concatenated slot m_v = [m | v] (dim 2*dim(var)): the reference runs
+ * gather(m_v) + TF elementwise ops + scatter_update(m_v) + scatter_sub(var);
+ * this is the same arithmetic, each op rounded separately, in one pass. */
+int kv_apply_adam(kv_table* var, kv_table* m_v, const int64_t* d_ids,
+                  const float* d_grad, int64_t n, const int32_t* d_n, float lr,
+                  float beta1, float beta2, float epsilon, float beta1_power,
+                  float beta2_power, uint16_t today, kv_stream stream);
+
+/* ---- dedup (stock TF ops on the path; TF 2.13 Unique / UnsortedSegmentSum) */
+
+int kv_workspace_create(kv_workspace** out);
+int kv_workspace_destroy(kv_workspace* ws);
+/* tf.unique / tf.unique_with_counts: d_uniq in first-occurrence order, d_idx
+ * int32 inverse, d_counts int32 or NULL, *d_num_unique int32 on the device.
+ * Call sites: python/ops/variable_scope.py:1096-1106 (TF
+ * _deduplicate_indexed_slices), python/ops/embedding_ops.py:365-372. */
+int kv_unique(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq,
+              int32_t* d_idx, int32_t* d_counts, int32_t* d_num_unique,
+              kv_stream stream);
+/* tf.math.unsorted_segment_sum(data[n, dim], idx, num_segments): d_out must
+ * hold max_segments rows; rows [0, *d_num_segments) are written (all
+ * max_segments rows when d_num_segments is NULL). */
+int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx,
+                   int64_t n, int dim, int64_t max_segments,
+                   const int32_t* d_num_segments, float* d_out, kv_stream stream);
+
+/* ---- checkpoint ---------------------------------------------------------- */
+
+/* KvVariable::ExportValues, kernels/dynamic_save.hpp:48-195, in two steps
+ * because the caller owns the output buffers: kv_export_count applies the
+ * under-threshold refresh (kernels/kv_variable.h:995-1012), counts, and
+ * synchronises `stream`; kv_export fills buffers of exactly those sizes (row
+ * order is unspecified, as in the reference).  d_freq_values is uint32 when
+ * freq_u32 else uint16.  Pointers for parts not exported may be NULL. */
+int kv_export_count(kv_table* t, int first_n, int enable_cutoff, float cutoff_value,
+                    kv_stream stream, int64_t* n_keys, int64_t* n_blacklist,
+                    int64_t* n_freq);
+int kv_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values,
+              int64_t* d_blacklist, int64_t* d_freq_keys, void* d_freq_values,
+              int freq_u32, kv_stream stream);
+/* KvVariable::ImportValues, kernels/dynamic_restore.hpp:156-262: clears the
+ * table, copies the rows (the reference aliases the input tensor), replaces
+ * the init table if init_rows > 0, marks the blacklist, overwrites frequency
+ * words of keys that exist.  Keys must be unique. */
+int kv_import(kv_table* t, const int64_t* d_keys, const float* d_values, int64_t n,
+              const float* d_init_table, int64_t init_rows,
+              const int64_t* d_blacklist, int64_t n_blacklist,
+              const int64_t* d_freq_keys, const void* d_freq_values, int64_t n_freq,
+              int freq_u32, kv_stream stream);
+
+/* ---- eviction ------------------------------------------------------------ */
+
+/* KvVariable::Delete, kernels/kv_variable.h:737-753. */
+int kv_delete(kv_table* t, const int64_t* d_ids, int64_t n, kv_stream stream);
+/* KvVariable::DeleteWithTimestamp, kernels/kv_variable.h:756-789: deletes keys
+ * with day > 0 and today - day >= threshold; writes up to `cap` deleted keys to
+ * d_out_keys (may be NULL) and the total to *n_deleted.  Synchronises. */
+int kv_delete_with_timestamp(kv_table* t, int threshold, uint16_t today,
+                             int64_t* d_out_keys, int64_t cap, kv_stream stream,
+                             int64_t* n_deleted);
+
+/* ---- multi-GPU routing (key-hash sharding; python/ops/embedding_ops.py:121-204
+ * does the same with floormod + dynamic_partition + dynamic_stitch) --------- */
+
+/* Groups ids by owner shard: d_sorted_ids[n] holds the ids of shard 0, then
+ * shard 1, ...; d_perm[n] (int32) maps each input position to its position in
+ * d_sorted_ids; d_shard_counts[num_shards] (int32).  mode 0: owner =
+ * mix64(id) % num_shards, mode 1: floormod(id, num_shards). */
+int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n,
+                     const int32_t* d_n, int num_shards, int mode,
+                     int64_t* d_sorted_ids, int32_t* d_perm, int32_t* d_shard_counts,
+                     kv_stream stream);
+/* out[i, :] = src[perm[i], :] (gather rows back into request order). */
+int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim,
+                    float* d_out, kv_stream stream);
+/* out[perm[i], :] = src[i, :]. */
+int kv_scatter_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim,
+                    float* d_out, kv_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVHBM_H_ */

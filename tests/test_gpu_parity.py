@@ -1,0 +1,410 @@
+"""GPU parity: the CUDA table driven through the C ABI vs the CPU oracle, same seeded
+inputs.  Bit-exact for membership, dedup indices, gathered rows, frequency words and flags;
+optimizer state within 1e-6 relative (north-star tolerance), stated at each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import binding as ob
+from tfplus_b200 import ops
+
+from kvtest_util import DEV, TODAY, Pair, t
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6   # north-star: optimizer-updated values and slots within 1e-6 relative
+ATOL = 1e-7
+
+
+@pytest.fixture(autouse=True)
+def _clock():
+  ops.set_today(TODAY)
+  yield
+  ops.set_today(None)
+
+
+def zipf_ids(n, universe, seed, s=1.1):
+  rng = np.random.default_rng(seed)
+  return (rng.zipf(s, size=n) % universe).astype(np.int64)
+
+
+# ----------------------------------------------------------------------------- lookups
+@pytest.mark.parametrize("dim", [1, 3, 8, 16, 32, 64, 128, 192, 256])
+def test_gather_or_insert_bit_exact(dim):
+  p = Pair(dim)
+  ids = zipf_ids(5000, 3000, seed=dim)
+  p.gather_or_insert(ids)            # all new, many duplicates inside the batch
+  p.gather_or_insert(ids[::-1].copy())  # all hits
+  more = np.concatenate([ids[:1000], np.arange(10**6, 10**6 + 700)])
+  p.gather_or_insert(more)           # mix of hits and new keys
+  g, w = p.gather_or_zeros(np.concatenate([more, [-1, -5, 2**40]]))
+  np.testing.assert_array_equal(g, w)
+  p.check_state()
+
+
+def test_gather_with_counts_and_saturation():
+  p = Pair(16, enter_threshold=3)
+  ids = np.array([5, 5, 5, 9, 9, 11, -1, 11, 5], np.int64)
+  counts = np.array([1, 70000, 2, 65535, 1, 0, 4, 3, 65000], np.int32)
+  p.gather_or_insert(ids, counts)
+  p.gather_or_insert(ids, counts)
+  p.check_state()
+  assert ops.kv_variable_frequency(p.gpu) == p.cpu.sum_freq()
+  got = ops.kv_variable_get_count_v2(p.gpu, t(np.array([5, 9, 11, -1, 12345], np.int64)))
+  assert got.cpu().tolist() == p.cpu.get_count([5, 9, 11, -1, 12345]).tolist()
+
+
+def test_frequency_kat_on_gpu():
+  # py_ut/tests/test_kv_variable_ops.py:150-189
+  p = Pair(8, enter_threshold=2)
+  p.gather_or_insert([0, 1, 2, 3, 4])
+  assert ops.kv_variable_frequency(p.gpu) == 0
+  p.gather_or_insert([2, 3, 4, 5, 6])
+  assert ops.kv_variable_frequency(p.gpu) == 6
+  p.gather_or_zeros([0, 1, 2, 3, 4])
+  assert ops.kv_variable_frequency(p.gpu) == 6
+
+
+def test_empty_and_shapes():
+  p = Pair(8)
+  out = ops.kv_variable_gather_or_insert_v2(p.gpu, torch.empty(0, dtype=torch.int64, device=DEV))
+  assert tuple(out.shape) == (0, 8)
+  assert ops.kv_variable_shape_v2(p.gpu) == [0, 8]
+  ids2d = torch.arange(12, device=DEV).reshape(3, 4)
+  assert tuple(ops.kv_variable_gather_or_insert_v2(p.gpu, ids2d).shape) == (3, 4, 8)
+  assert ops.kv_variable_size_v2(p.gpu) == 12
+
+
+def test_growth_from_default_capacity():
+  p = Pair(32)
+  rng = np.random.default_rng(5)
+  for step in range(4):
+    ids = rng.integers(-2**62, 2**62, size=60000)
+    p.gather_or_insert(ids)
+  p.check_state()
+  assert ops.kv_variable_size_v2(p.gpu) == p.cpu.size() >= 239000
+
+
+def test_scatter_exact_answers_and_parity():
+  # kernels/kv_variable_test.cc:272-356 on the GPU, then random parity
+  p = Pair(64, init=1.0)
+  ids = np.arange(10)
+  one, two = np.ones((10, 64), np.float32), np.full((10, 64), 2.0, np.float32)
+  for op, upd, want in [("update", one, 1.0), ("add", one, 2.0), ("sub", one, 1.0),
+                        ("mul", two, 2.0), ("div", two, 1.0), ("min", two, 1.0),
+                        ("max", two, 2.0)]:
+    p.scatter(op, ids, upd)
+    g, w = p.gather_or_zeros(ids)
+    assert (g == want).all() and (w == want).all(), op
+  q = Pair(24)
+  rng = np.random.default_rng(1)
+  for op in ["add", "update", "sub", "mul", "div", "min", "max"]:
+    ids = rng.permutation(400)[:300]
+    q.scatter(op, ids, rng.normal(size=(300, 24)).astype(np.float32))
+  q.check_state()
+
+
+def test_insert_or_update_with_masks():
+  p = Pair(16)
+  ids = np.arange(100)
+  vals = np.random.default_rng(2).normal(size=(100, 16)).astype(np.float32)
+  vals[7] = 0.0  # under-threshold row
+  filt = (ids % 3 == 0).astype(np.uint8)
+  black = (ids % 5 == 1).astype(np.uint8)
+  p.insert(ids, vals, filt, black)
+  p.check_state()
+  p.insert(ids, vals + 1)  # overwrite everything, blacklisted keys stay blacklisted
+  p.check_state()
+  g, w = p.gather_or_zeros(ids)
+  np.testing.assert_array_equal(g, w)
+
+
+# ----------------------------------------------------------------------------- dedup
+@pytest.mark.parametrize("n", [1, 31, 1000, 65536, 200001])
+def test_unique_bit_exact(n):
+  ids = zipf_ids(n, 10**7, seed=n) - 3
+  uniq, idx, counts = ops.unique(t(ids), with_counts=True)
+  ou, oi, oc = ob.unique(ids, with_counts=True)
+  np.testing.assert_array_equal(uniq.cpu().numpy(), ou)
+  np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+  np.testing.assert_array_equal(counts.cpu().numpy(), oc)
+  assert idx.dtype == torch.int32
+
+
+@pytest.mark.parametrize("dim", [1, 16, 64, 100, 256])
+def test_segment_sum(dim):
+  n = 20000
+  ids = zipf_ids(n, 5000, seed=3)
+  data = np.random.default_rng(4).normal(size=(n, dim)).astype(np.float32)
+  ou, oi = ob.unique(ids)
+  got = ops.unsorted_segment_sum(t(data), t(oi), ou.size).cpu().numpy()
+  want = ob.segment_sum(data, oi, ou.size)
+  # summation order differs (north-star: only uniq/idx are bit-exact)
+  np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------- optimizers
+def _steps(n_steps, universe, batch, dim, seed):
+  rng = np.random.default_rng(seed)
+  for s in range(n_steps):
+    ids = (rng.zipf(1.2, size=batch) % universe).astype(np.int64)
+    u, idx = ob.unique(ids)
+    g = ob.segment_sum(rng.normal(size=(batch, dim)).astype(np.float32), idx, u.size)
+    yield ids, u, g
+
+
+@pytest.mark.parametrize("dim,l1,l2,l21", [(64, 0., 0., 0.), (64, 1e-5, 1e-5, 1e-5),
+                                           (16, 1e-3, 1e-2, 1e-3), (1, 0., 0., 0.),
+                                           (256, 1e-5, 1e-5, 1e-5), (12, 0., 1e-4, 0.)])
+def test_group_adam_v4(dim, l1, l2, l21):
+  var = Pair(dim, enter_threshold=2)
+  slot = Pair(3 * dim, init=0.0)
+  b1, b2, lr, eps = 0.9, 0.999, 1e-2, 1e-8
+  b1p, b2p = b1, b2
+  for ids, u, g in _steps(6, 2000, 3000, dim, seed=dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_group_sparse_apply_adam_v4(var.gpu, slot.gpu, t(g), t(u), lr, b1p, b2p, b1, b2,
+                                               eps, l1, l2, l21)
+    ob.apply_group_adam_v4(var.cpu, slot.cpu, u, g, lr, b1p, b2p, b1, b2, eps, l1, l2, l21,
+                           today=TODAY)
+    b1p *= b1
+    b2p *= b2
+  var.check_state(rtol=RTOL, atol=ATOL)
+  slot.check_state(rtol=RTOL, atol=ATOL)
+
+
+def test_group_adam_blacklist_and_revive():
+  # strong group lasso: most rows fall under tau and are blacklisted (training_ops.cc:7189-7191),
+  # read back as zeros (table_manager.h:224-226) and revive at zeros (kv_variable.h:406-408)
+  dim = 32
+  var = Pair(dim, init=0.01)
+  slot = Pair(3 * dim, init=0.0)
+  rng = np.random.default_rng(9)
+  b1p, b2p = 0.9, 0.999
+  n_black = 0
+  for step in range(5):
+    ids = rng.permutation(500)[:300].astype(np.int64)
+    scale = 10.0 if step % 2 else 0.01
+    g = (rng.normal(size=(300, dim)) * scale).astype(np.float32)
+    got, want = var.gather_or_insert(ids)
+    ops.kv_variable_group_sparse_apply_adam_v4(var.gpu, slot.gpu, t(g), t(ids), 0.05, b1p, b2p, 0.9,
+                                               0.999, 1e-8, 0.0, 0.0, 0.5)
+    ob.apply_group_adam_v4(var.cpu, slot.cpu, ids, g, 0.05, b1p, b2p, 0.9, 0.999, 1e-8, 0.0, 0.0,
+                           0.5, today=TODAY)
+    b1p *= 0.9
+    b2p *= 0.999
+    gs, cs = var.check_state(rtol=RTOL, atol=ATOL)
+    n_black = max(n_black, len(cs["black"]))
+    slot.check_state(rtol=RTOL, atol=ATOL)
+  assert n_black > 50
+
+
+@pytest.mark.parametrize("dim,update_slots", [(64, True), (1, True), (20, False)])
+def test_adagrad(dim, update_slots):
+  var = Pair(dim, enter_threshold=2)
+  acc = Pair(dim, init=0.1)
+  for ids, u, g in _steps(5, 1500, 2500, dim, seed=100 + dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_sparse_apply_adagrad(var.gpu, acc.gpu, 0.05, t(g), t(u),
+                                         update_slots=update_slots)
+    ob.apply_adagrad(var.cpu, acc.cpu, u, g, 0.05, update_slots, today=TODAY)
+  var.check_state(rtol=RTOL, atol=ATOL)
+  acc.check_state(rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dim,l1,l2,l21,l2s,lrp", [(16, 0., 0., 0., 0., -0.5),
+                                                   (16, 1e-5, 1e-5, 1e-5, 0., -0.5),
+                                                   (64, 0.01, 0.05, 0.05, 0., -0.5),
+                                                   (32, 1e-3, 1e-3, 1e-3, 1e-3, -0.5),
+                                                   (8, 1e-4, 0., 1e-4, 0., -0.6)])
+def test_sparse_group_ftrl(dim, l1, l2, l21, l2s, lrp):
+  var = Pair(dim, enter_threshold=1)
+  acc = Pair(dim, init=0.1)
+  lin = Pair(dim, init=0.0)
+  tol = dict(rtol=RTOL, atol=ATOL) if lrp == -0.5 else dict(rtol=2e-5, atol=1e-6)  # powf vs pow
+  for ids, u, g in _steps(5, 1500, 2500, dim, seed=200 + dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_sparse_group_sparse_apply_ftrl_v2(var.gpu, acc.gpu, lin.gpu, t(g), t(u), 0.1, l1,
+                                                      l2, l21, l2s, lrp)
+    ob.apply_sparse_group_ftrl(var.cpu, acc.cpu, lin.cpu, u, g, 0.1, l1, l2, l21, l2s, lrp,
+                               today=TODAY)
+  var.check_state(**tol)
+  acc.check_state(**tol)
+  lin.check_state(**tol)
+
+
+def test_adam_scatter_path_is_bit_exact():
+  # the reference's own Adam route: gather(m_v) + torch elementwise + scatter_update + scatter_sub
+  dim = 32
+  var = Pair(dim)
+  mv = Pair(2 * dim, init=0.0)
+  lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-8
+  b1p, b2p = b1, b2
+  f = torch.float32
+  for ids, u, g in _steps(4, 800, 1200, dim, seed=7):
+    var.gather_or_insert(ids)
+    tu, tg = t(u), t(g)
+    m_v = ops.kv_variable_gather_or_insert_v2(mv.gpu, tu)
+    m, v = m_v[:, :dim], m_v[:, dim:]
+    m_t = torch.tensor(b1, dtype=f, device=DEV) * m + tg * torch.tensor(1 - np.float32(b1), device=DEV)
+    v_t = torch.tensor(b2, dtype=f, device=DEV) * v + (tg * tg) * torch.tensor(1 - np.float32(b2), device=DEV)
+    ops.kv_variable_scatter_update_v2(mv.gpu, tu, torch.cat([m_t, v_t], 1))
+    lr_t = (np.float32(lr) * np.sqrt(np.float32(1) - np.float32(b2p))) / (np.float32(1) - np.float32(b1p))
+    upd = (torch.tensor(lr_t, device=DEV) * m_t) / (torch.tensor(np.float32(eps), device=DEV) + torch.sqrt(v_t))
+    ops.kv_variable_scatter_sub_v2(var.gpu, tu, upd)
+    ob.adam_step(var.cpu, mv.cpu, u, g, lr, b1, b2, eps, b1p, b2p, today=TODAY)
+    b1p *= b1
+    b2p *= b2
+  var.check_state()
+  mv.check_state()
+
+
+def test_fused_adam_matches_scatter_path():
+  dim = 64
+  var = Pair(dim)
+  mv = Pair(2 * dim, init=0.0)
+  lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-8
+  b1p, b2p = b1, b2
+  for ids, u, g in _steps(4, 800, 1200, dim, seed=8):
+    var.gather_or_insert(ids)
+    ops.kv_variable_sparse_apply_adam(var.gpu, mv.gpu, t(g), t(u), lr, b1, b2, eps, b1p, b2p)
+    ob.adam_step(var.cpu, mv.cpu, u, g, lr, b1, b2, eps, b1p, b2p, today=TODAY)
+    b1p *= b1
+    b2p *= b2
+  var.check_state()   # same separately-rounded ops: bit-exact
+  mv.check_state()
+
+
+def test_apply_reads_count_from_device():
+  dim = 16
+  var = Pair(dim)
+  acc = Pair(dim, init=0.1)
+  ids = np.arange(1000, dtype=np.int64)
+  g = np.random.default_rng(3).normal(size=(1000, dim)).astype(np.float32)
+  n_dev = torch.tensor([600], dtype=torch.int32, device=DEV)
+  ops.kv_variable_sparse_apply_adagrad(var.gpu, acc.gpu, 0.1, t(g), t(ids), num_indices=n_dev)
+  ob.apply_adagrad(var.cpu, acc.cpu, ids[:600], g[:600], 0.1, today=TODAY)
+  var.check_state(rtol=RTOL, atol=ATOL)
+  acc.check_state(rtol=RTOL, atol=ATOL)
+
+
+# ----------------------------------------------------------------------------- checkpoint / eviction
+@pytest.mark.parametrize("first_n,exp", [(3, (0, 5)), (4, (1, 6)), (6, (1, 6))])
+def test_import_export_shape_kat_on_gpu(first_n, exp):
+  # py_ut/tests/test_kv_variable_ops.py:345-435
+  D, R = 8, 1024
+  h = ops.kv_variable(value_shape=[D], enter_threshold=1, device=DEV)
+  init = torch.randn(R, D, device=DEV)
+  ops.init_kv_variable_v2(h, init)
+  vals = torch.stack([torch.full((D,), float(x)) for x in range(5)]).to(DEV)
+  ops.kv_variable_import(h, torch.arange(5), vals, init, torch.tensor([7]),
+                         torch.tensor([1, 2, 3, 4, 5]),
+                         torch.tensor([1, 2, 3, 4, 5], dtype=torch.int32).to(torch.uint16),
+                         first_n=first_n)
+  out = ops.kv_variable_export(h, first_n=6)
+  assert len(out) == 6
+  shapes = [tuple(x.shape) for x in out]
+  assert shapes == [(5,), (5, D), (R, D), (exp[0],), (exp[1],), (exp[1],)]
+  assert out[5].dtype == torch.uint16
+
+
+def test_export_import_round_trip():
+  dim = 16
+  var = Pair(dim, enter_threshold=2)
+  slot = Pair(3 * dim, init=0.0)
+  b1p, b2p = 0.9, 0.999
+  for ids, u, g in _steps(4, 600, 900, dim, seed=21):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_group_sparse_apply_adam_v4(var.gpu, slot.gpu, t(g), t(u), 0.02, b1p, b2p, 0.9,
+                                               0.999, 1e-8, 1e-4, 1e-4, 2e-2)
+    ob.apply_group_adam_v4(var.cpu, slot.cpu, u, g, 0.02, b1p, b2p, 0.9, 0.999, 1e-8, 1e-4, 1e-4,
+                           2e-2, today=TODAY)
+    b1p *= 0.9
+    b2p *= 0.999
+  before = var.state_gpu()
+  k, v, it, bl, fk, fv = ops.kv_variable_export(var.gpu, first_n=6, enable_cutoff=True,
+                                                cutoff_value=1e-20)
+  e = var.cpu.export(first_n=6, enable_cutoff=True, cutoff_value=1e-20)
+  # restore into fresh tables on both sides
+  fresh = Pair(dim, enter_threshold=2, init=0.5)
+  ops.kv_variable_import(fresh.gpu, k, v, it, bl, fk, fv, first_n=6)
+  fresh.cpu.import_(e["keys"], e["values"], e["init_table"], e["blacklist"], e["freq_keys"],
+                    e["freq_values"].astype(np.uint32))
+  after, _ = fresh.check_state(rtol=RTOL, atol=ATOL)
+  assert set(after["rows"]) == set(before["rows"]) and after["black"] == before["black"]
+  for key, row in before["rows"].items():
+    np.testing.assert_array_equal(after["rows"][key], row)
+  # u16 frequency table: the day is lost on restore, the count survives
+  for key, w in before["freq"].items():
+    assert after["freq"][key] == (w & 0xFFFF)
+  # new keys after restore use the imported init table
+  fresh.gather_or_insert(np.arange(10**6, 10**6 + 50))
+
+
+def test_export_first_n_variants_and_cutoff():
+  p = Pair(8, enter_threshold=2)
+  p.gather_or_insert([1, 2, 3, 3, 4, 4])
+  p.scatter("update", [2], np.zeros((1, 8), np.float32))   # all-zero row -> under threshold
+  for first_n in (2, 3, 4, 5, 6):
+    for cut in ((True, 1e-20), (False, 0.0), (True, 0.5)):
+      g = ops.kv_variable_export(p.gpu, first_n=first_n, enable_cutoff=cut[0], cutoff_value=cut[1])
+      c = p.cpu.export(first_n=first_n, enable_cutoff=cut[0], cutoff_value=cut[1])
+      assert sorted(g[0].cpu().tolist()) == sorted(c["keys"].tolist()), (first_n, cut)
+      if first_n > 2:
+        assert sorted(g[3].cpu().tolist()) == sorted(c["blacklist"].tolist())
+        assert sorted(g[4].cpu().tolist()) == sorted(c["freq_keys"].tolist())
+        assert tuple(g[2].shape) == c["init_table"].shape
+  rk, rv = ops.read_kv_variable_op_v2(p.gpu)
+  assert sorted(rk.cpu().tolist()) == [1, 2, 3, 4]
+
+
+def test_delete_and_reuse():
+  p = Pair(16)
+  p.gather_or_insert(np.arange(1000))
+  ops.kv_variable_delete(p.gpu, t(np.arange(0, 1000, 2)))
+  p.cpu.delete(np.arange(0, 1000, 2))
+  p.check_state()
+  assert ops.kv_variable_size_v2(p.gpu) == 500
+  p.gather_or_insert(np.arange(0, 1500, 3))   # deleted keys come back through the free list
+  p.check_state()
+  g, w = p.gather_or_zeros(np.arange(1500))
+  np.testing.assert_array_equal(g, w)
+
+
+def test_delete_with_timestamp():
+  p = Pair(8)
+  ops.set_today(TODAY - 10)
+  p.cpu.gather_or_insert(np.arange(100), today=TODAY - 10)
+  ops.kv_variable_gather_or_insert_v2(p.gpu, t(np.arange(100)))
+  ops.set_today(TODAY)
+  p.gather_or_insert(np.arange(50, 150))
+  p.scatter("add", np.arange(200, 220), np.ones((20, 8), np.float32))  # day 0: never evicted
+  got = ops.kv_variable_delete_with_timestamp(p.gpu, 5)
+  want = p.cpu.delete_with_timestamp(5, TODAY)
+  assert sorted(got.cpu().tolist()) == sorted(want.tolist()) == list(range(50))
+  p.check_state()
+
+
+def test_errors():
+  h = ops.kv_variable(value_shape=[8], device=DEV)
+  s = ops.kv_variable(value_shape=[8], device=DEV)
+  with pytest.raises(RuntimeError, match="uninitialized"):
+    ops.kv_variable_sparse_apply_adagrad(h, s, 0.1, torch.zeros(2, 8, device=DEV),
+                                         torch.arange(2, device=DEV))
+  ops.init_kv_variable_v2(h, torch.ones(4, 8, device=DEV))
+  ops.init_kv_variable_v2(s, torch.ones(4, 8, device=DEV))
+  with pytest.raises(ValueError, match="lr is not a positive scalar"):
+    ops.kv_variable_group_sparse_apply_adam_v4(h, s, torch.zeros(2, 8, device=DEV),
+                                               torch.arange(2, device=DEV), 0.0, .9, .999, .9, .999,
+                                               1e-8, 0, 0, 0)
+  with pytest.raises(ValueError, match="same shape"):
+    ops.kv_variable_group_sparse_apply_adam_v4(h, s, torch.zeros(2, 8, device=DEV),
+                                               torch.arange(2, device=DEV), 0.1, .9, .999, .9, .999,
+                                               1e-8, 0, 0, 0)
+  with pytest.raises(ValueError, match="counts dtype must be int32"):
+    ops.kv_variable_gather_or_insert_with_counts(h, torch.arange(2, device=DEV),
+                                                 torch.ones(2, dtype=torch.int64))
+  ops.destroy_kv_variable_op_v2(h)
+  assert not ops.kv_variable_is_initialized_v2(h)
+  with pytest.raises(RuntimeError, match="NotFound"):
+    ops.kv_variable_gather_or_zeros_v2(h, torch.arange(2, device=DEV))

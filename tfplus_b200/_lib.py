@@ -1,0 +1,96 @@
+"""ctypes loader of libkvhbm.so, the C ABI declared in include/kvhbm.h.
+
+There is no CPU fallback: if the library has not been built, or no CUDA device
+is present when a table is created, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkvhbm.so")
+
+KV_OK = 0
+_STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: NotImplementedError, 4: MemoryError,
+               5: RuntimeError}
+_STATUS_NAME = {1: "InvalidArgument", 2: "FailedPrecondition", 3: "Unimplemented",
+                4: "ResourceExhausted", 5: "Internal"}
+
+vp, i64, i32, f32, u16, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint16, C.c_uint64
+
+# name -> argtypes (every function returns int unless listed in _RESTYPE)
+SIGNATURES = {
+    "kv_last_error": [],
+    "kv_launch_count": [],
+    "kv_create": [i32, i32, i64, C.POINTER(vp)],
+    "kv_destroy": [vp],
+    "kv_dim": [vp],
+    "kv_enter_threshold": [vp],
+    "kv_set_seed": [vp, u64],
+    "kv_reserve": [vp, i64, vp],
+    "kv_set_init_table": [vp, vp, i64, vp],
+    "kv_is_initialized": [vp, C.POINTER(i32)],
+    "kv_init_table_rows": [vp, C.POINTER(i64)],
+    "kv_get_init_table": [vp, vp, vp],
+    "kv_size": [vp, vp, C.POINTER(i64)],
+    "kv_sum_freq": [vp, vp, C.POINTER(i64)],
+    "kv_map_size": [vp, vp, C.POINTER(i64)],
+    "kv_gather_or_insert": [vp, vp, vp, i64, vp, u16, vp],
+    "kv_gather_or_zeros": [vp, vp, i64, vp, vp],
+    "kv_insert_or_update": [vp, vp, vp, i64, vp, vp, vp],
+    "kv_scatter": [vp, i32, vp, vp, i64, vp],
+    "kv_get_count": [vp, vp, i64, vp, vp],
+    "kv_get_timestamp": [vp, vp, i64, vp, u16, vp],
+    "kv_apply_adagrad": [vp, vp, vp, vp, i64, vp, f32, i32, u16, vp],
+    "kv_apply_group_adam_v4": [vp, vp, vp, vp, i64, vp] + [f32] * 9 + [u16, vp],
+    "kv_apply_sparse_group_ftrl": [vp, vp, vp, vp, vp, i64, vp] + [f32] * 6 + [u16, vp],
+    "kv_apply_adam": [vp, vp, vp, vp, i64, vp] + [f32] * 6 + [u16, vp],
+    "kv_workspace_create": [C.POINTER(vp)],
+    "kv_workspace_destroy": [vp],
+    "kv_unique": [vp, vp, i64, vp, vp, vp, vp, vp],
+    "kv_segment_sum": [vp, vp, vp, i64, i32, i64, vp, vp, vp],
+    "kv_export_count": [vp, i32, i32, f32, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
+    "kv_export": [vp, i32, vp, vp, vp, vp, vp, i32, vp],
+    "kv_import": [vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, vp],
+    "kv_delete": [vp, vp, i64, vp],
+    "kv_delete_with_timestamp": [vp, i32, u16, vp, i64, vp, C.POINTER(i64)],
+    "kv_partition_ids": [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp],
+    "kv_permute_rows": [vp, vp, i64, i32, vp, vp],
+    "kv_scatter_rows": [vp, vp, i64, i32, vp, vp],
+}
+_RESTYPE = {"kv_last_error": C.c_char_p, "kv_launch_count": i64}
+
+_lib = None
+
+
+class KvError(RuntimeError):
+  pass
+
+
+def load():
+  """Returns the loaded library; raises if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        "tfplus_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; "
+        "g.build()'` (or python tfplus_b200/build.py); there is no CPU fallback." % LIB_PATH)
+  lib = C.CDLL(LIB_PATH)
+  for name, args in SIGNATURES.items():
+    fn = getattr(lib, name)
+    fn.argtypes = args
+    fn.restype = _RESTYPE.get(name, C.c_int)
+  _lib = lib
+  return lib
+
+
+def check(status):
+  if status == KV_OK:
+    return
+  msg = load().kv_last_error().decode("utf-8", "replace")
+  exc = _STATUS_EXC.get(status, RuntimeError)
+  raise exc("%s: %s" % (_STATUS_NAME.get(status, "status %d" % status), msg))
+
+
+def launch_count():
+  return int(load().kv_launch_count())

@@ -1,0 +1,482 @@
+// apply.cu — fused per-row sparse optimizer updates on the device table.
+//
+// One kernel per optimizer step: for every (unique) id it finds-or-inserts the
+// value row and the slot row(s), reads gradient + value + slots once, updates
+// them in registers and writes them back once — the reference walks each row
+// three times through lazy Eigen expressions and two or three hash maps
+// (training_ops.cc:7166-7195, :713-751, :1473-1482).
+//
+// Arithmetic is the reference's, operation by operation, in fp32 without FMA
+// contraction (this file is compiled with -fmad=false; sqrtf and `/` are the
+// IEEE-rounded versions).  Only the L2-norm reduction order differs (a tile
+// butterfly instead of Eigen's packet reduction).
+#include "table.h"
+
+namespace kvhbm {
+
+enum { K_ADAGRAD = 0, K_GROUP_ADAM = 1, K_FTRL = 2, K_ADAM = 3 };
+
+struct ApplyParams {
+  float lr;
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, epsilon;
+  float alpha;      // GroupAdam: lr*sqrt(1-b2^t)/(1-b1^t); Adam: lr_t
+  float l1, l2x2;   // l1 (scaled), 2*l2 (scaled)
+  float l21_norm;   // l21 * sqrt(D)
+  float shrink2;    // 2 * l2_shrinkage
+  float neg_lr_power;
+  int later_step;   // beta1 > beta1_power
+  int update_slots;
+  int fast_sqrt;    // lr_power == -0.5
+};
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+constexpr int V_SKIP = -1;   // low-frequency key or padding: nothing happens
+constexpr int V_ZERO = 0;    // blacklisted key revived at zeros (table_manager.h:359-372)
+constexpr int V_COPY = 1;
+constexpr int V_CLAIM = 3;   // key inserted by this lane: row starts at the initializer
+constexpr int V_KEEP = 4;    // Adam path only: blacklisted var is left alone (kv_variable.h:690)
+
+template <int KIND> struct Kind;
+template <> struct Kind<K_ADAGRAD> { static constexpr int PARTS = 1; static constexpr bool TWO = false; };
+template <> struct Kind<K_GROUP_ADAM> { static constexpr int PARTS = 3; static constexpr bool TWO = false; };
+template <> struct Kind<K_FTRL> { static constexpr int PARTS = 2; static constexpr bool TWO = true; };
+template <> struct Kind<K_ADAM> { static constexpr int PARTS = 2; static constexpr bool TWO = false; };
+
+__device__ __forceinline__ float powp(const ApplyParams& p, float x) {
+  return p.fast_sqrt ? sqrtf(x) : powf(x, p.neg_lr_power);
+}
+__device__ __forceinline__ float clip_l1(float lin, float l1) {
+  // linear.cwiseMin(l1).cwiseMax(-l1) with Eigen's mini/maxi
+  float a = l1 < lin ? l1 : lin;
+  return a < -l1 ? -l1 : a;
+}
+
+// Per-lane probe of one slot-variable table: FindOrInsertUnsafe(key, ctx, nullptr),
+// kv_variable.h:382-416 (found: freq += 1, day = today; absent: ctor freq 1).
+template <int KIND>
+__device__ __forceinline__ int probe_slot_table(const TableView& t, long long key, uint32_t today,
+                                                long long* pos, uint32_t* ctl) {
+  Slot s;
+  bool claimed;
+  *pos = find_or_claim(t, key, &s, &claimed);
+  if (*pos < 0) return V_SKIP;
+  if (claimed) {
+    *ctl = alloc_row(t);
+    // Adam reaches its slot through GatherOrInsert: insert_func writes {1, today}
+    t.slots[*pos].freq = KIND == K_ADAM ? ((1u << 16) | today) : (1u << 16);
+    return V_CLAIM;
+  }
+  *ctl = s.ctl;
+  add_frequency(&t.slots[*pos].freq, 1u, today);
+  return V_COPY;
+}
+
+template <int VEC, int CPL, int UNR, int KIND>
+__global__ void __launch_bounds__(128)
+apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restrict__ ids,
+             const float* __restrict__ grad, long long n, const int* __restrict__ d_n,
+             ApplyParams p, uint32_t today, int tpr) {
+  constexpr int PARTS = Kind<KIND>::PARTS;
+  constexpr bool TWO = Kind<KIND>::TWO;
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long nwarps = gridDim.x * wpb;
+  const int kpi = 32 / tpr;
+  const int tl = lane & (tpr - 1);
+  const int tq = lane / tpr;
+  const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int dim = var.dim;
+  if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
+
+  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? ids[i] : 0;
+
+    // ---------------- phase 1: one lane per id ----------------
+    int vmode = V_SKIP, amode = V_SKIP, bmode = V_SKIP;
+    long long vpos = -1, apos = -1, bpos = -1;
+    uint32_t vctl = 0, actl = 0, bctl = 0;
+    if (valid) {
+      Slot s;
+      bool claimed;
+      vpos = find_or_claim(var, key, &s, &claimed);
+      if (vpos >= 0) {
+        if (claimed) {
+          vctl = alloc_row(var);
+          var.slots[vpos].freq = 1u << 16;
+          vmode = V_CLAIM;
+        } else {
+          vctl = s.ctl;
+          if (KIND != K_ADAM && freq_count(s.freq) < var.enter_threshold) vmode = V_SKIP;
+          else if (vctl & CTL_BLACK) vmode = KIND == K_ADAM ? V_KEEP : V_ZERO;
+          else vmode = V_COPY;
+        }
+      }
+      if (vmode != V_SKIP) {
+        amode = probe_slot_table<KIND>(sa, key, today, &apos, &actl);
+        if (TWO) bmode = probe_slot_table<KIND>(sb, key, today, &bpos, &bctl);
+      }
+    }
+    float* vrow = vmode != V_SKIP ? row_ptr(var, vctl) : nullptr;
+    float* arow = amode != V_SKIP ? row_ptr(sa, actl) : nullptr;
+    float* brow = (TWO && bmode != V_SKIP) ? row_ptr(sb, bctl) : nullptr;
+
+    // verdicts collected by each id's owner lane
+    bool v_under = (vctl & CTL_UNDER) != 0, a_under = (actl & CTL_UNDER) != 0,
+         b_under = (bctl & CTL_UNDER) != 0;
+    bool v_black = false;
+
+    // ---------------- phase 2: tiles move and update rows ----------------
+    for (int it = 0; it < tpr; it += UNR) {
+      Chunk<VEC> g[UNR][CPL], w[UNR][CPL], s[UNR][PARTS][CPL];
+      int vm[UNR], am[UNR], bm[UNR];
+      float *vp[UNR], *ap[UNR], *bp[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        vm[u] = V_SKIP; am[u] = V_SKIP; bm[u] = V_SKIP;
+        vp[u] = ap[u] = bp[u] = nullptr;
+        if (it + u < tpr) {
+          const int kl = (it + u) * kpi + tq;
+          vm[u] = __shfl_sync(FULL, vmode, kl);
+          am[u] = __shfl_sync(FULL, amode, kl);
+          vp[u] = shfl_ptr(vrow, kl);
+          ap[u] = shfl_ptr(arow, kl);
+          if (TWO) { bm[u] = __shfl_sync(FULL, bmode, kl); bp[u] = shfl_ptr(brow, kl); }
+          const long long k = shfl_ll(key, kl);
+          const bool on = vm[u] != V_SKIP;
+          long long v1 = -1, v2 = -1, a1 = -1, a2 = -1, b1 = -1, b2 = -1;
+          if (vm[u] == V_CLAIM) init_rows_of(var, k, &v1, &v2);
+          if (am[u] == V_CLAIM) init_rows_of(sa, k, &a1, &a2);
+          if (TWO && bm[u] == V_CLAIM) init_rows_of(sb, k, &b1, &b2);
+          const float* gp = grad + (base + kl) * (long long)dim;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            const bool in = on && off < dim;
+            if (in) g[u][q].load_stream(gp + off); else chunk_zero(g[u][q]);
+            if (in && (vm[u] == V_COPY || vm[u] == V_KEEP)) w[u][q].load_cg(vp[u] + off);
+            else if (in && vm[u] == V_CLAIM) init_chunk<VEC>(var, v1, v2, off, w[u][q]);
+            else chunk_zero(w[u][q]);
+#pragma unroll
+            for (int r = 0; r < PARTS; ++r) {
+              const bool second = TWO && r == 1;
+              const int md = second ? bm[u] : am[u];
+              float* rp = second ? bp[u] : ap[u];
+              const int soff = (TWO ? 0 : r * dim) + off;
+              if (in && md == V_COPY) s[u][r][q].load_cg(rp + soff);
+              else if (in && md == V_CLAIM) {
+                if (second) init_chunk<VEC>(sb, b1, b2, soff, s[u][r][q]);
+                else init_chunk<VEC>(sa, a1, a2, soff, s[u][r][q]);
+              } else chunk_zero(s[u][r][q]);
+            }
+          }
+        }
+      }
+
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (it + u >= tpr) continue;  // uniform across the warp
+        const bool on = vm[u] != V_SKIP;
+        bool vbig = false, abig = false, bbig = false, black = false;
+
+        if (KIND == K_ADAGRAD) {
+          // training_ops.cc:1473-1482.  Under-threshold flags are those of the
+          // insert (kv_variable.h:398), Adagrad never refreshes them.
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
+            abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const float gg = g[u][q].v[e];
+              float a = s[u][0][q].v[e];
+              if (p.update_slots) a += gg * gg;
+              s[u][0][q].v[e] = a;
+              if (dim > 1) w[u][q].v[e] -= (p.lr * gg) * (1.0f / sqrtf(a));
+              else w[u][q].v[e] -= (p.lr * gg) / sqrtf(a);
+            }
+          }
+        } else if (KIND == K_ADAM) {
+          // python/training/adam.py:116-156, every TF op rounded on its own
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const float gg = g[u][q].v[e];
+              const float m_t = (s[u][0][q].v[e] * p.beta1) + (gg * p.one_minus_beta1);
+              const float v_t = (s[u][1][q].v[e] * p.beta2) + ((gg * gg) * p.one_minus_beta2);
+              s[u][0][q].v[e] = m_t;
+              s[u][1][q].v[e] = v_t;
+              if (vm[u] != V_KEEP) w[u][q].v[e] -= (p.alpha * m_t) / (sqrtf(v_t) + p.epsilon);
+            }
+            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
+            abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF) |
+                    chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF);
+          }
+        } else {
+          // GroupAdam v4 (training_ops.cc:7166-7195) / SparseGroupFtrl (:713-751)
+          Chunk<VEC> z[CPL], den[CPL], gs[CPL];
+          float ss = 0.f;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const float gg = g[u][q].v[e];
+              const float wv = w[u][q].v[e];
+              float lin;
+              if (KIND == K_GROUP_ADAM) {
+                const float m = p.beta1 * s[u][0][q].v[e] + p.one_minus_beta1 * gg;
+                const float vo = s[u][1][q].v[e];
+                const float nv = p.beta2 * vo + p.one_minus_beta2 * (gg * gg);
+                const float sq = sqrtf(nv);
+                lin = s[u][2][q].v[e];
+                if (p.later_step) lin += p.alpha * m - (sq - sqrtf(vo)) * wv;
+                else lin += p.alpha * m - (sq + p.epsilon) * wv;
+                s[u][0][q].v[e] = m;
+                s[u][1][q].v[e] = nv;
+                s[u][2][q].v[e] = lin;
+                den[q].v[e] = sq + p.epsilon + p.l2x2;
+              } else {
+                const float a = s[u][0][q].v[e];
+                const float gsh = gg + p.shrink2 * wv;
+                const float na = a + gsh * gsh;
+                const float pna = powp(p, na);
+                lin = s[u][1][q].v[e];
+                lin += gsh - (pna - powp(p, a)) / p.lr * wv;
+                s[u][1][q].v[e] = lin;
+                gs[q].v[e] = gsh;
+                den[q].v[e] = pna / p.lr + p.l2x2;
+              }
+              const float zz = clip_l1(lin, p.l1) - lin;
+              z[q].v[e] = zz;
+              ss += zz * zz;
+            }
+          }
+          for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+          const float nrm = sqrtf(ss);
+          black = !(nrm > p.l21_norm);
+          const float c = 1.0f - p.l21_norm / nrm;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              const float w_old = w[u][q].v[e];
+              if (!black) w[u][q].v[e] = z[q].v[e] * c / den[q].v[e];
+              if (KIND == K_FTRL) {
+                // accum += grad_to_use.square(), re-evaluated with the new var
+                // (old var after a blacklist); see oracle/kv_oracle.cc
+                const float g2 = black ? gs[q].v[e] : g[u][q].v[e] + p.shrink2 * w[u][q].v[e];
+                s[u][0][q].v[e] += g2 * g2;
+                (void)w_old;
+              }
+            }
+            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
+            if (KIND == K_GROUP_ADAM) {
+              abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF) |
+                      chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF) |
+                      chunk_over_cutoff(s[u][2][q], DEFAULT_CUTOFF);
+            } else {
+              abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF);
+              bbig |= chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF);
+            }
+          }
+        }
+
+        // write back
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (on && off < dim) {
+            if (vm[u] != V_KEEP) w[u][q].store(vp[u] + off);
+#pragma unroll
+            for (int r = 0; r < PARTS; ++r) {
+              const bool second = TWO && r == 1;
+              float* rp = second ? bp[u] : ap[u];
+              s[u][r][q].store(rp + (TWO ? 0 : r * dim) + off);
+            }
+          }
+        }
+        const unsigned vb = __ballot_sync(FULL, vbig);
+        const unsigned ab = __ballot_sync(FULL, abig);
+        const unsigned bb = TWO ? __ballot_sync(FULL, bbig) : 0u;
+        const unsigned kb = __ballot_sync(FULL, black);
+        if (lane / kpi == it + u) {
+          const int sh = (lane % kpi) * tpr;
+          v_under = ((vb >> sh) & tmask) == 0;
+          a_under = ((ab >> sh) & tmask) == 0;
+          b_under = ((bb >> sh) & tmask) == 0;
+          v_black = ((kb >> sh) & 1u) != 0;
+        }
+      }
+    }
+
+    // ---------------- phase 3: publish flags ----------------
+    if (vmode != V_SKIP) {
+      // value row
+      uint32_t nv = CTL_READY | (vctl & CTL_ROW_MASK);
+      if (KIND == K_ADAGRAD) {
+        if (vmode == V_CLAIM) nv |= v_under ? CTL_UNDER : 0u;       // insert-time flag
+        else if (vmode == V_ZERO) nv |= CTL_UNDER;                   // RemoveBlacklistUnsafe
+        else nv |= vctl & CTL_UNDER;                                 // untouched
+      } else if (KIND == K_ADAM) {
+        if (vmode == V_KEEP) nv = vctl;
+        else nv |= v_under ? CTL_UNDER : 0u;                         // ScatterUpdate refresh
+      } else {
+        if (v_black) nv |= CTL_BLACK | CTL_UNDER;                    // MarkBlacklistUnsafe
+        else nv |= v_under ? CTL_UNDER : 0u;                         // CoverUpdateUnsafe
+      }
+      if (vmode == V_CLAIM) __threadfence();
+      if (nv != vctl || vmode == V_CLAIM) var.slots[vpos].ctl = nv;
+
+      uint32_t na = CTL_READY | (actl & CTL_ROW_MASK);
+      if (KIND == K_ADAGRAD) na |= amode == V_CLAIM ? (a_under ? CTL_UNDER : 0u) : (actl & CTL_UNDER);
+      else na |= a_under ? CTL_UNDER : 0u;
+      if (amode == V_CLAIM) __threadfence();
+      if (na != actl || amode == V_CLAIM) sa.slots[apos].ctl = na;
+
+      if (TWO) {
+        uint32_t nb = CTL_READY | (bctl & CTL_ROW_MASK) | (b_under ? CTL_UNDER : 0u);
+        if (bmode == V_CLAIM) __threadfence();
+        if (nb != bctl || bmode == V_CLAIM) sb.slots[bpos].ctl = nb;
+      }
+    }
+  }
+}
+
+template <int VEC, int CPL, int KIND>
+int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
+                 int64_t n, const int32_t* d_n, const ApplyParams& p, uint16_t today,
+                 cudaStream_t st, int tpr) {
+  constexpr int UNR = CPL == 1 ? 4 : (CPL == 2 ? 2 : 1);
+  const int blocks = blocks_for(n, 128, var->device, 16);
+  TableView vb = sb ? sb->view() : sa->view();
+  apply_kernel<VEC, CPL, UNR, KIND><<<blocks, 128, 0, st>>>(
+      var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,
+      today, tpr);
+  KV_LAUNCHED();
+  return 0;
+}
+
+template <int KIND>
+int dispatch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
+                   int64_t n, const int32_t* d_n, const ApplyParams& p, uint16_t today,
+                   cudaStream_t st) {
+  if (n <= 0) return 0;
+  KV_TRY(var->ensure(n, st));
+  KV_TRY(sa->ensure(n, st));
+  if (sb) KV_TRY(sb->ensure(n, st));
+  RowGeom g = row_geom(var->dim);
+  const int cpl = g.cpl == 3 ? 4 : g.cpl;
+#define CALL(V, C) launch_apply<V, C, KIND>(var, sa, sb, ids, grad, n, d_n, p, today, st, g.tpr)
+  if (g.vec == 4) {
+    if (cpl == 1) return CALL(4, 1);
+    if (cpl == 2) return CALL(4, 2);
+    return CALL(4, 4);
+  }
+  if (cpl == 1) return CALL(1, 1);
+  if (cpl == 2) return CALL(1, 2);
+  return CALL(1, 4);
+#undef CALL
+}
+
+int check_initialized(const Table* t, const char* what) {
+  if (!t->initialized)
+    return fail(2, std::string("Attempting to use uninitialized variables: ") + what);
+  return 0;
+}
+
+}  // namespace
+
+int do_apply_adagrad(Table* var, Table* accum, const int64_t* ids, const float* grad, int64_t n,
+                     const int32_t* d_n, float lr, int update_slots, uint16_t today,
+                     cudaStream_t st) {
+  KV_TRY(check_initialized(var, "var"));
+  KV_TRY(check_initialized(accum, "accum"));
+  if (accum->dim != var->dim)
+    return fail(1, "var and accum do not have the same shape");
+  ApplyParams p{};
+  p.lr = lr;
+  p.update_slots = update_slots;
+  return dispatch_apply<K_ADAGRAD>(var, accum, nullptr, ids, grad, n, d_n, p, today, st);
+}
+
+int do_apply_group_adam_v4(Table* var, Table* mvl, const int64_t* ids, const float* grad,
+                           int64_t n, const int32_t* d_n, float lr, float beta1_power,
+                           float beta2_power, float beta1, float beta2, float epsilon, float l1,
+                           float l2, float l21, uint16_t today, cudaStream_t st) {
+  // argument checks of training_ops.cc:7001-7103
+  KV_TRY(check_initialized(var, "var"));
+  KV_TRY(check_initialized(mvl, "m_v_linear"));
+  if (!(lr > 0.f)) return fail(1, "lr is not a positive scalar");
+  if (!(l1 >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
+  if (!(l2 >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
+  if (!(l21 >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
+  if (mvl->dim != 3 * var->dim)
+    return fail(1, "kv_variable and linear do not have the same shape");
+  ApplyParams p{};
+  p.lr = lr;
+  p.beta1 = beta1;
+  p.beta2 = beta2;
+  p.one_minus_beta1 = 1.0f - beta1;
+  p.one_minus_beta2 = 1.0f - beta2;
+  p.epsilon = epsilon;
+  const float l1s = l1 * lr, l2s = l2 * lr, l21s = l21 * lr;  // :7111-7113
+  p.l1 = l1s;
+  p.l2x2 = 2.0f * l2s;
+  p.alpha = lr * sqrtf(1.0f - beta2_power) / (1.0f - beta1_power);  // :7117-7119
+  p.l21_norm = l21s * sqrtf(static_cast<float>(var->dim));           // :7120
+  p.later_step = beta1 > beta1_power;                                 // :7171
+  return dispatch_apply<K_GROUP_ADAM>(var, mvl, nullptr, ids, grad, n, d_n, p, today, st);
+}
+
+int do_apply_sparse_group_ftrl(Table* var, Table* accum, Table* linear, const int64_t* ids,
+                               const float* grad, int64_t n, const int32_t* d_n, float lr,
+                               float l1, float l2, float l21, float l2_shrinkage, float lr_power,
+                               uint16_t today, cudaStream_t st) {
+  // argument checks of training_ops.cc:560-659
+  KV_TRY(check_initialized(var, "var"));
+  KV_TRY(check_initialized(accum, "accum"));
+  KV_TRY(check_initialized(linear, "linear"));
+  if (!(lr > 0.f)) return fail(1, "lr is not a positive scalar");
+  if (!(l1 >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
+  if (!(l2 >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
+  if (!(l21 >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
+  if (!(l2_shrinkage >= 0.f))
+    return fail(1, "l2 shrinkage regularization strength is not a non-negative scalar");
+  if (!(lr_power <= 0.f)) return fail(1, "lr_power is not a non-positive scalar");
+  if (accum->dim != var->dim) return fail(1, "kv_varaible and accum do not have the same shape");
+  if (linear->dim != var->dim) return fail(1, "kv_variable and linear do not have the same shape");
+  ApplyParams p{};
+  p.lr = lr;
+  p.l1 = l1;
+  p.l2x2 = 2.0f * l2;
+  p.l21_norm = l21 * sqrtf(static_cast<float>(var->dim));
+  p.shrink2 = 2.0f * l2_shrinkage;
+  p.neg_lr_power = -lr_power;
+  p.fast_sqrt = lr_power == -0.5f;
+  return dispatch_apply<K_FTRL>(var, accum, linear, ids, grad, n, d_n, p, today, st);
+}
+
+int do_apply_adam(Table* var, Table* mv, const int64_t* ids, const float* grad, int64_t n,
+                  const int32_t* d_n, float lr, float beta1, float beta2, float epsilon,
+                  float beta1_power, float beta2_power, uint16_t today, cudaStream_t st) {
+  KV_TRY(check_initialized(var, "var"));
+  KV_TRY(check_initialized(mv, "m_v"));
+  if (mv->dim != 2 * var->dim) return fail(1, "m_v slot must have dim 2 * dim(var)");
+  ApplyParams p{};
+  p.lr = lr;
+  p.beta1 = beta1;
+  p.beta2 = beta2;
+  p.one_minus_beta1 = 1.0f - beta1;
+  p.one_minus_beta2 = 1.0f - beta2;
+  p.epsilon = epsilon;
+  p.alpha = (lr * sqrtf(1.0f - beta2_power)) / (1.0f - beta1_power);  // adam.py:147-148
+  return dispatch_apply<K_ADAM>(var, mv, nullptr, ids, grad, n, d_n, p, today, st);
+}
+
+}  // namespace kvhbm

@@ -1,0 +1,351 @@
+// capi.cu — the extern "C" surface declared in include/kvhbm.h.
+#include "../../include/kvhbm.h"
+
+#include <string>
+
+#include "table.h"
+
+namespace kvhbm {
+struct Workspace;
+const std::string& last_error();
+long long launch_count();
+Workspace* workspace_new();
+void workspace_delete(Workspace*);
+
+int do_gather(Table*, bool insert, const int64_t*, const int32_t*, int64_t, float*, uint16_t,
+              cudaStream_t);
+int do_scatter(Table*, int op, const int64_t*, const float*, int64_t, cudaStream_t);
+int do_insert(Table*, const int64_t*, const float*, int64_t, const uint8_t*, const uint8_t*,
+              cudaStream_t);
+int do_get_count(Table*, const int64_t*, int64_t, int32_t*, cudaStream_t);
+int do_get_timestamp(Table*, const int64_t*, int64_t, uint32_t*, uint16_t, cudaStream_t);
+int do_permute_rows(bool scatter, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
+
+int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*, float,
+                     int, uint16_t, cudaStream_t);
+int do_apply_group_adam_v4(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
+                           float, float, float, float, float, float, float, float, float, uint16_t,
+                           cudaStream_t);
+int do_apply_sparse_group_ftrl(Table*, Table*, Table*, const int64_t*, const float*, int64_t,
+                               const int32_t*, float, float, float, float, float, float, uint16_t,
+                               cudaStream_t);
+int do_apply_adam(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*, float,
+                  float, float, float, float, float, uint16_t, cudaStream_t);
+
+int do_unique(Workspace*, const int64_t*, int64_t, int64_t*, int32_t*, int32_t*, int32_t*,
+              cudaStream_t);
+int do_segment_sum(Workspace*, const float*, const int32_t*, int64_t, int, int64_t, const int32_t*,
+                   float*, cudaStream_t);
+int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, int, int64_t*,
+                     int32_t*, int32_t*, cudaStream_t);
+
+int do_stats(Table*, cudaStream_t, int64_t*, int64_t*, int64_t*);
+int do_export_count(Table*, int, int, float, cudaStream_t, int64_t*, int64_t*, int64_t*);
+int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cudaStream_t);
+int do_import(Table*, const int64_t*, const float*, int64_t, const float*, int64_t, const int64_t*,
+              int64_t, const int64_t*, const void*, int64_t, int, cudaStream_t);
+int do_delete(Table*, const int64_t*, int64_t, cudaStream_t);
+int do_delete_older(Table*, int, uint16_t, int64_t*, int64_t, cudaStream_t, int64_t*);
+
+// InitRandomValues: only the first call takes effect unless `force` (import).
+int do_set_init_table(Table* tb, const float* d_table, int64_t rows, cudaStream_t st, bool force) {
+  if (!force && tb->initialized && tb->init_rows > 0) return 0;
+  if (rows < 0 || (rows > 0 && d_table == nullptr))
+    return fail(1, "init table must be [rows, dim] in device memory");
+  float* n = nullptr;
+  if (rows > 0) {
+    KV_CUDA(cudaMalloc(&n, (size_t)rows * tb->dim * sizeof(float)));
+    KV_CUDA(cudaMemcpyAsync(n, d_table, (size_t)rows * tb->dim * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  }
+  if (tb->d_init) {
+    KV_CUDA(cudaStreamSynchronize(st));  // kernels in flight may still read the old table
+    cudaFree(tb->d_init);
+  }
+  tb->d_init = n;
+  tb->init_rows = rows;
+  tb->initialized = true;
+  return 0;
+}
+}  // namespace kvhbm
+
+using namespace kvhbm;
+
+struct kv_table { Table t; };
+struct kv_workspace { Workspace* w; };
+
+namespace {
+inline cudaStream_t S(kv_stream s) { return static_cast<cudaStream_t>(s); }
+
+// Every entry point runs on the table's device and under the table's mutex
+// (TF may call one kernel object from several executor threads).
+struct Guard {
+  std::unique_lock<std::mutex> l;
+  int rc = 0;
+  explicit Guard(kv_table* t) {
+    if (!t) { rc = fail(KV_INVALID_ARGUMENT, "null table handle"); return; }
+    l = std::unique_lock<std::mutex>(t->t.mu);
+    cudaError_t e = cudaSetDevice(t->t.device);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
+  }
+};
+#define KV_ENTER(t)      \
+  Guard _g(t);           \
+  if (_g.rc) return _g.rc
+#define KV_NEED(cond, msg) \
+  if (!(cond)) return fail(KV_INVALID_ARGUMENT, msg)
+}  // namespace
+
+extern "C" {
+
+const char* kv_last_error(void) { return last_error().c_str(); }
+int64_t kv_launch_count(void) { return launch_count(); }
+
+int kv_create(int dim, int enter_threshold, int64_t capacity_hint, kv_table** out) {
+  KV_NEED(out != nullptr, "kv_create: out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KV_INTERNAL, "kvhbm needs a CUDA device: there is no CPU fallback");
+  }
+  kv_table* t = new kv_table();
+  int rc = t->t.create(dim, enter_threshold, capacity_hint);
+  if (rc) { delete t; return rc; }
+  *out = t;
+  return KV_OK;
+}
+int kv_destroy(kv_table* t) {
+  if (!t) return KV_OK;
+  cudaSetDevice(t->t.device);
+  cudaDeviceSynchronize();
+  delete t;
+  return KV_OK;
+}
+int kv_dim(const kv_table* t) { return t ? t->t.dim : -1; }
+int kv_enter_threshold(const kv_table* t) { return t ? (int)t->t.enter_threshold : -1; }
+int kv_set_seed(kv_table* t, uint64_t seed) {
+  KV_ENTER(t);
+  t->t.seed = seed;
+  return KV_OK;
+}
+int kv_reserve(kv_table* t, int64_t n_keys, kv_stream stream) {
+  KV_ENTER(t);
+  Table& tb = t->t;
+  KV_TRY(tb.ensure(n_keys, S(stream)));
+  // ensure() books the keys as used; a reservation does not insert anything
+  tb.used_ub -= (uint64_t)n_keys;
+  tb.rows_ub -= (uint64_t)n_keys;
+  return KV_OK;
+}
+int kv_set_init_table(kv_table* t, const float* d_table, int64_t rows, kv_stream stream) {
+  KV_ENTER(t);
+  return do_set_init_table(&t->t, d_table, rows, S(stream), false);
+}
+int kv_is_initialized(const kv_table* t, int* out) {
+  KV_NEED(t && out, "kv_is_initialized: null argument");
+  *out = t->t.initialized ? 1 : 0;
+  return KV_OK;
+}
+int kv_init_table_rows(const kv_table* t, int64_t* rows) {
+  KV_NEED(t && rows, "kv_init_table_rows: null argument");
+  *rows = t->t.init_rows;
+  return KV_OK;
+}
+int kv_get_init_table(const kv_table* t, float* d_out, kv_stream stream) {
+  KV_NEED(t != nullptr, "null table handle");
+  if (t->t.init_rows == 0) return KV_OK;
+  KV_CUDA(cudaMemcpyAsync(d_out, t->t.d_init, (size_t)t->t.init_rows * t->t.dim * sizeof(float),
+                          cudaMemcpyDeviceToDevice, S(stream)));
+  return KV_OK;
+}
+int kv_size(kv_table* t, kv_stream stream, int64_t* out) {
+  KV_ENTER(t);
+  return do_stats(&t->t, S(stream), out, nullptr, nullptr);
+}
+int kv_sum_freq(kv_table* t, kv_stream stream, int64_t* out) {
+  KV_ENTER(t);
+  return do_stats(&t->t, S(stream), nullptr, out, nullptr);
+}
+int kv_map_size(kv_table* t, kv_stream stream, int64_t* out) {
+  KV_ENTER(t);
+  return do_stats(&t->t, S(stream), nullptr, nullptr, out);
+}
+
+int kv_gather_or_insert(kv_table* t, const int64_t* d_ids, const int32_t* d_counts, int64_t n,
+                        float* d_out, uint16_t today, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_insert: bad arguments");
+  return do_gather(&t->t, true, d_ids, d_counts, n, d_out, today, S(stream));
+}
+int kv_gather_or_zeros(kv_table* t, const int64_t* d_ids, int64_t n, float* d_out,
+                       kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_zeros: bad arguments");
+  return do_gather(&t->t, false, d_ids, nullptr, n, d_out, 0, S(stream));
+}
+int kv_insert_or_update(kv_table* t, const int64_t* d_ids, const float* d_values, int64_t n,
+                        const uint8_t* d_filter_out, const uint8_t* d_blacklist,
+                        kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_values)), "insert_or_update: bad arguments");
+  return do_insert(&t->t, d_ids, d_values, n, d_filter_out, d_blacklist, S(stream));
+}
+int kv_scatter(kv_table* t, int op, const int64_t* d_ids, const float* d_updates, int64_t n,
+               kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_updates)), "scatter: bad arguments");
+  return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream));
+}
+int kv_get_count(kv_table* t, const int64_t* d_ids, int64_t n, int32_t* d_out, kv_stream stream) {
+  KV_ENTER(t);
+  return do_get_count(&t->t, d_ids, n, d_out, S(stream));
+}
+int kv_get_timestamp(kv_table* t, const int64_t* d_ids, int64_t n, uint32_t* d_out,
+                     uint16_t today, kv_stream stream) {
+  KV_ENTER(t);
+  return do_get_timestamp(&t->t, d_ids, n, d_out, today, S(stream));
+}
+
+// The apply ops take the mutexes of all their tables in address order, as
+// MaybeLockVariableInputMutexesInOrder does (training_ops.cc:131-184).
+namespace {
+struct MultiGuard {
+  std::unique_lock<std::mutex> l[3];
+  int rc = 0;
+  MultiGuard(kv_table* a, kv_table* b, kv_table* c) {
+    kv_table* v[3] = {a, b, c};
+    int k = c ? 3 : 2;
+    for (int i = 0; i < k; ++i)
+      if (!v[i]) { rc = fail(KV_INVALID_ARGUMENT, "null table handle"); return; }
+    for (int i = 0; i < k; ++i)
+      for (int j = i + 1; j < k; ++j) {
+        if (v[i] == v[j]) { rc = fail(KV_INVALID_ARGUMENT, "apply: var and slot are the same table"); return; }
+        if (v[j] < v[i]) { kv_table* x = v[i]; v[i] = v[j]; v[j] = x; }
+      }
+    for (int i = 0; i < k; ++i) l[i] = std::unique_lock<std::mutex>(v[i]->t.mu);
+    cudaError_t e = cudaSetDevice(a->t.device);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
+  }
+};
+}  // namespace
+
+int kv_apply_adagrad(kv_table* var, kv_table* accum, const int64_t* d_ids, const float* d_grad,
+                     int64_t n, const int32_t* d_n, float lr, int update_slots, uint16_t today,
+                     kv_stream stream) {
+  MultiGuard g(var, accum, nullptr);
+  if (g.rc) return g.rc;
+  return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, lr, update_slots, today,
+                          S(stream));
+}
+int kv_apply_group_adam_v4(kv_table* var, kv_table* mvl, const int64_t* d_ids,
+                           const float* d_grad, int64_t n, const int32_t* d_n, float lr,
+                           float beta1_power, float beta2_power, float beta1, float beta2,
+                           float epsilon, float l1, float l2, float l21, uint16_t today,
+                           kv_stream stream) {
+  MultiGuard g(var, mvl, nullptr);
+  if (g.rc) return g.rc;
+  return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, lr, beta1_power,
+                                beta2_power, beta1, beta2, epsilon, l1, l2, l21, today, S(stream));
+}
+int kv_apply_sparse_group_ftrl(kv_table* var, kv_table* accum, kv_table* linear,
+                               const int64_t* d_ids, const float* d_grad, int64_t n,
+                               const int32_t* d_n, float lr, float l1, float l2, float l21,
+                               float l2_shrinkage, float lr_power, uint16_t today,
+                               kv_stream stream) {
+  MultiGuard g(var, accum, linear);
+  if (g.rc) return g.rc;
+  return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, lr, l1,
+                                    l2, l21, l2_shrinkage, lr_power, today, S(stream));
+}
+int kv_apply_adam(kv_table* var, kv_table* m_v, const int64_t* d_ids, const float* d_grad,
+                  int64_t n, const int32_t* d_n, float lr, float beta1, float beta2, float epsilon,
+                  float beta1_power, float beta2_power, uint16_t today, kv_stream stream) {
+  MultiGuard g(var, m_v, nullptr);
+  if (g.rc) return g.rc;
+  return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, lr, beta1, beta2, epsilon,
+                       beta1_power, beta2_power, today, S(stream));
+}
+
+int kv_workspace_create(kv_workspace** out) {
+  KV_NEED(out != nullptr, "kv_workspace_create: out is null");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KV_INTERNAL, "kvhbm needs a CUDA device: there is no CPU fallback");
+  }
+  kv_workspace* w = new kv_workspace();
+  w->w = workspace_new();
+  *out = w;
+  return KV_OK;
+}
+int kv_workspace_destroy(kv_workspace* ws) {
+  if (!ws) return KV_OK;
+  workspace_delete(ws->w);
+  delete ws;
+  return KV_OK;
+}
+int kv_unique(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq, int32_t* d_idx,
+              int32_t* d_counts, int32_t* d_num_unique, kv_stream stream) {
+  KV_NEED(ws && d_num_unique && (n == 0 || (d_ids && d_uniq && d_idx)), "unique: bad arguments");
+  return do_unique(ws->w, d_ids, n, d_uniq, d_idx, d_counts, d_num_unique, S(stream));
+}
+int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx, int64_t n, int dim,
+                   int64_t max_segments, const int32_t* d_num_segments, float* d_out,
+                   kv_stream stream) {
+  KV_NEED(ws && (n == 0 || (d_data && d_idx)) && (max_segments == 0 || d_out),
+          "segment_sum: bad arguments");
+  return do_segment_sum(ws->w, d_data, d_idx, n, dim, max_segments, d_num_segments, d_out,
+                        S(stream));
+}
+
+int kv_export_count(kv_table* t, int first_n, int enable_cutoff, float cutoff_value,
+                    kv_stream stream, int64_t* n_keys, int64_t* n_blacklist, int64_t* n_freq) {
+  KV_ENTER(t);
+  KV_NEED(n_keys && n_blacklist && n_freq, "export_count: null output");
+  return do_export_count(&t->t, first_n, enable_cutoff, cutoff_value, S(stream), n_keys,
+                         n_blacklist, n_freq);
+}
+int kv_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_t* d_blacklist,
+              int64_t* d_freq_keys, void* d_freq_values, int freq_u32, kv_stream stream) {
+  KV_ENTER(t);
+  return do_export(&t->t, first_n, d_keys, d_values, d_blacklist, d_freq_keys, d_freq_values,
+                   freq_u32, S(stream));
+}
+int kv_import(kv_table* t, const int64_t* d_keys, const float* d_values, int64_t n,
+              const float* d_init_table, int64_t init_rows, const int64_t* d_blacklist,
+              int64_t n_blacklist, const int64_t* d_freq_keys, const void* d_freq_values,
+              int64_t n_freq, int freq_u32, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && n_blacklist >= 0 && n_freq >= 0, "import: negative size");
+  return do_import(&t->t, d_keys, d_values, n, d_init_table, init_rows, d_blacklist, n_blacklist,
+                   d_freq_keys, d_freq_values, n_freq, freq_u32, S(stream));
+}
+int kv_delete(kv_table* t, const int64_t* d_ids, int64_t n, kv_stream stream) {
+  KV_ENTER(t);
+  return do_delete(&t->t, d_ids, n, S(stream));
+}
+int kv_delete_with_timestamp(kv_table* t, int threshold, uint16_t today, int64_t* d_out_keys,
+                             int64_t cap, kv_stream stream, int64_t* n_deleted) {
+  KV_ENTER(t);
+  return do_delete_older(&t->t, threshold, today, d_out_keys, cap, S(stream), n_deleted);
+}
+
+int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n, const int32_t* d_n,
+                     int num_shards, int mode, int64_t* d_sorted_ids, int32_t* d_perm,
+                     int32_t* d_shard_counts, kv_stream stream) {
+  KV_NEED(ws && d_shard_counts && (n == 0 || (d_ids && d_sorted_ids && d_perm)),
+          "partition_ids: bad arguments");
+  return do_partition_ids(ws->w, d_ids, n, d_n, num_shards, mode, d_sorted_ids, d_perm,
+                          d_shard_counts, S(stream));
+}
+int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
+                    kv_stream stream) {
+  return do_permute_rows(false, d_src, d_perm, n, dim, d_out, S(stream));
+}
+int kv_scatter_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
+                    kv_stream stream) {
+  return do_permute_rows(true, d_src, d_perm, n, dim, d_out, S(stream));
+}
+
+}  // extern "C"

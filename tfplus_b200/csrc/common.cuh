@@ -1,0 +1,277 @@
+// common.cuh — device-side layout of the HBM-resident KvVariable table and the
+// helpers every kernel shares (hash, probe, row-tile geometry, initializer).
+//
+// Layout (DESIGN.md "Data layout in HBM"):
+//   slots : Slot[capacity]    16 B each, open addressing, linear probing,
+//                             capacity a power of two, load factor <= 0.5
+//   rows  : float[n_rows][row_stride]   densely packed row arena (a CUDA
+//                             virtual-memory reservation that grows in place)
+// A slot is {int64 key, u32 freq, u32 ctl}:
+//   freq = count << 16 | day   (the reference packs lo16 = count, hi16 = day,
+//                               embedding_value.h:229-234; swapped here so a
+//                               plain atomicAdd on the word can only carry out
+//                               of the top, never into the day)
+//   ctl  = READY | BLACK | UNDER | row index (29 bits)
+#ifndef KVHBM_COMMON_CUH_
+#define KVHBM_COMMON_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kvhbm {
+
+constexpr long long KEY_EMPTY = (long long)0x8000000000000000ULL;
+constexpr long long KEY_TOMB = (long long)0x8000000000000001ULL;
+
+constexpr uint32_t CTL_READY = 0x80000000u;  // row contents are published
+constexpr uint32_t CTL_BLACK = 0x40000000u;  // EmbeddingValue::in_black_
+constexpr uint32_t CTL_UNDER = 0x20000000u;  // EmbeddingValue::under_threshold_
+constexpr uint32_t CTL_ROW_MASK = 0x1FFFFFFFu;
+
+constexpr float DEFAULT_CUTOFF = 1.0e-20f;  // kv_variable_interface.h:55
+
+struct __align__(16) Slot {
+  long long key;
+  uint32_t freq;
+  uint32_t ctl;
+};
+
+struct Counters {
+  unsigned long long used;       // slots ever claimed since the last rehash (live + tombstones)
+  unsigned long long rows_bump;  // rows handed out by the bump allocator
+  long long free_top;            // entries on the free-row stack
+  unsigned long long tombstones;
+  unsigned long long scratch[4];  // per-call reduction results (size, sum_freq, export counts)
+};
+
+// What a kernel needs to know about one table; passed by value.
+struct TableView {
+  Slot* slots;
+  unsigned long long mask;  // capacity - 1
+  int shift;                // 64 - log2(capacity)
+  float* rows;
+  int dim;
+  int row_stride;  // floats, multiple of 4
+  const float* init;
+  long long init_rows;
+  unsigned long long seed;
+  uint32_t enter_threshold;
+  Counters* ctr;
+  uint32_t* free_rows;
+};
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+constexpr unsigned long long GOLDEN = 0x9e3779b97f4a7c15ULL;
+
+__device__ __forceinline__ unsigned long long home_slot(const TableView& t, long long key) {
+  return mix64((unsigned long long)key) >> t.shift;
+}
+
+// ---- memory access helpers -------------------------------------------------
+__device__ __forceinline__ Slot load_slot(const Slot* p) {
+  // L2-coherent 128-bit load: slots change under concurrent inserts.
+  int4 v = __ldcg(reinterpret_cast<const int4*>(p));
+  Slot s;
+  s.key = (long long)(((unsigned long long)(uint32_t)v.y << 32) | (uint32_t)v.x);
+  s.freq = (uint32_t)v.z;
+  s.ctl = (uint32_t)v.w;
+  return s;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- probing ------------------------------------------------------------------
+// Read-only lookup.  Returns the slot index or -1.
+__device__ __forceinline__ long long find_slot(const TableView& t, long long key, Slot* out) {
+  unsigned long long pos = home_slot(t, key);
+  for (unsigned long long probes = 0; probes <= t.mask; ++probes) {
+    Slot s = load_slot(t.slots + pos);
+    if (s.key == key) { *out = s; return (long long)pos; }
+    if (s.key == KEY_EMPTY) return -1;
+    pos = (pos + 1) & t.mask;
+  }
+  return -1;
+}
+
+// Find-or-claim.  Returns the slot index; *claimed is true when this thread
+// won the atomicCAS on an empty slot (it must then allocate a row, fill it and
+// publish ctl).  A thread that loses the race to the same key gets
+// claimed=false and may see ctl without CTL_READY.
+__device__ __forceinline__ long long find_or_claim(const TableView& t, long long key,
+                                                   Slot* out, bool* claimed) {
+  unsigned long long pos = home_slot(t, key);
+  *claimed = false;
+  for (unsigned long long probes = 0; probes <= t.mask; ++probes) {
+    Slot s = load_slot(t.slots + pos);
+    if (s.key == key) { *out = s; return (long long)pos; }
+    if (s.key == KEY_EMPTY) {
+      unsigned long long old = atomicCAS(
+          reinterpret_cast<unsigned long long*>(&t.slots[pos].key),
+          (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      if (old == (unsigned long long)KEY_EMPTY) {
+        atomicAdd(&t.ctr->used, 1ULL);
+        *claimed = true;
+        out->key = key; out->freq = 0; out->ctl = 0;
+        return (long long)pos;
+      }
+      if (old == (unsigned long long)key) {
+        out->key = key; out->freq = 0; out->ctl = 0;  // caller re-reads ctl
+        return (long long)pos;
+      }
+    }
+    pos = (pos + 1) & t.mask;
+  }
+  return -1;  // table full: the host sizing guarantees this cannot happen
+}
+
+// Row allocator: pop the free stack (filled only by delete kernels, which never
+// run concurrently with this), else bump.
+__device__ __forceinline__ uint32_t alloc_row(const TableView& t) {
+  if (t.free_rows != nullptr) {
+    long long top = atomicAdd(reinterpret_cast<unsigned long long*>(&t.ctr->free_top),
+                              (unsigned long long)(-1LL));
+    if (top > 0) return t.free_rows[top - 1];
+    atomicAdd(reinterpret_cast<unsigned long long*>(&t.ctr->free_top), 1ULL);
+  }
+  return (uint32_t)atomicAdd(&t.ctr->rows_bump, 1ULL);
+}
+
+__device__ __forceinline__ float* row_ptr(const TableView& t, uint32_t ctl) {
+  return t.rows + (size_t)(ctl & CTL_ROW_MASK) * (size_t)t.row_stride;
+}
+
+// ---- frequency word --------------------------------------------------------------
+// freq = count << 16 | day.  Saturating add of `cnt` (<= 65535) to the count and
+// day := today, using only native atomics (no CAS loop, so thousands of
+// duplicates of one hot key do not serialise on retries):
+//  * atomicAdd(cnt << 16): a carry leaves the word at the top, the day is safe;
+//  * whoever sees old_count + cnt > 65535 pins the count to 0xFFFF with an
+//    atomicOr.  Every add after the last such OR would itself overflow and OR
+//    again, so once any add overflowed the final count is 0xFFFF, and
+//    otherwise it is the exact sum: min(65535, sum) as utility.h:65-70;
+//  * the day changes once per key per day: only then AND it out and OR it in
+//    (all writers of one launch write the same `today`).
+__device__ __forceinline__ void add_frequency(uint32_t* freq, uint32_t cnt, uint32_t today) {
+  uint32_t old = atomicAdd(freq, cnt << 16);
+  if ((old >> 16) + cnt > 0xFFFFu) atomicOr(freq, 0xFFFF0000u);
+  if ((old & 0xFFFFu) != today) {
+    atomicAnd(freq, 0xFFFF0000u);
+    atomicOr(freq, today);
+  }
+}
+// SaturateMaxFrequency, utility.h:47-49 (including its wrap of negative counts).
+__device__ __forceinline__ uint32_t saturate_count(int c) {
+  return (uint32_t)(uint16_t)(c < 65535 ? c : 65535);
+}
+__host__ __device__ __forceinline__ uint32_t freq_count(uint32_t w) { return w >> 16; }
+__host__ __device__ __forceinline__ uint32_t freq_day(uint32_t w) { return w & 0xFFFFu; }
+// reference packing: lo16 = count, hi16 = day
+__host__ __device__ __forceinline__ uint32_t freq_to_ref(uint32_t w) { return (w << 16) | (w >> 16); }
+
+// ---- row tiles ----------------------------------------------------------------------
+// A row of `dim` floats is moved by a tile of `tpr` lanes (power of two <= 32),
+// each lane owning `CPL` chunks of VEC floats: chunk c of lane l covers floats
+// [(c * tpr + l) * VEC, +VEC).  VEC = 4 (128-bit) when dim % 4 == 0, else 1.
+struct RowGeom {
+  int vec;  // 4 or 1
+  int tpr;  // lanes per row
+  int cpl;  // chunks per lane
+};
+inline RowGeom row_geom(int dim) {
+  RowGeom g;
+  g.vec = (dim % 4 == 0) ? 4 : 1;
+  int nvec = dim / g.vec;
+  int tpr = 1;
+  while (tpr < nvec && tpr < 32) tpr <<= 1;
+  g.tpr = tpr;
+  g.cpl = (nvec + tpr - 1) / tpr;
+  return g;
+}
+
+template <int VEC> struct Chunk;
+template <> struct Chunk<4> {
+  float v[4];
+  __device__ __forceinline__ void load_cg(const float* p) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void load_nc(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void load_stream(const float* p) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ __forceinline__ void store_stream(float* p) const {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <> struct Chunk<1> {
+  float v[1];
+  __device__ __forceinline__ void load_cg(const float* p) { v[0] = __ldcg(p); }
+  __device__ __forceinline__ void load_nc(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void load_stream(const float* p) { v[0] = __ldcs(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+  __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, v[0]); }
+};
+template <int VEC>
+__device__ __forceinline__ void chunk_zero(Chunk<VEC>& c) {
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) c.v[k] = 0.f;
+}
+
+// Deterministic replacement of GenerateRandomInitialValue (kv_variable.h:889-898):
+// r = mix64(key ^ seed [^ GOLDEN]) % R instead of std::rand() % R; the
+// arithmetic (t[r1] + t[r2]) * 0.5f is the reference's.
+__device__ __forceinline__ void init_rows_of(const TableView& t, long long key,
+                                             long long* r1, long long* r2) {
+  if (t.init_rows <= 0) { *r1 = -1; *r2 = -1; return; }
+  unsigned long long k = (unsigned long long)key ^ t.seed;
+  *r1 = (long long)(mix64(k) % (unsigned long long)t.init_rows);
+  *r2 = (long long)(mix64(k ^ GOLDEN) % (unsigned long long)t.init_rows);
+}
+template <int VEC>
+__device__ __forceinline__ void init_chunk(const TableView& t, long long r1, long long r2,
+                                           int off, Chunk<VEC>& c) {
+  if (r1 < 0) { chunk_zero(c); return; }
+  Chunk<VEC> a, b;
+  a.load_nc(t.init + r1 * t.dim + off);
+  b.load_nc(t.init + r2 * t.dim + off);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) c.v[k] = (a.v[k] + b.v[k]) * 0.5f;
+}
+template <int VEC>
+__device__ __forceinline__ bool chunk_over_cutoff(const Chunk<VEC>& c, float cutoff) {
+  bool big = false;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) big |= (fabsf(c.v[k]) >= cutoff);
+  return big;
+}
+
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+  int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffLL), src);
+  int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
+  return ((long long)hi << 32) | (unsigned int)lo;
+}
+template <typename T>
+__device__ __forceinline__ T* shfl_ptr(T* p, int src) {
+  return reinterpret_cast<T*>(shfl_ll((long long)p, src));
+}
+
+}  // namespace kvhbm
+#endif  // KVHBM_COMMON_CUH_

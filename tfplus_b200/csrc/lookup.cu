@@ -1,0 +1,525 @@
+// lookup.cu — find-or-insert / gather, scatter-update, insert-or-update.
+//
+// Kernel shape shared by everything here: a warp takes 32 ids.  Phase 1, one
+// lane per id: hash, probe the 16-byte slots (all 32 probes of the warp are in
+// flight together), claim an empty slot with atomicCAS when inserting.  Phase
+// 2, the warp moves the 32 rows cooperatively: a row is split over a tile of
+// `tpr` lanes doing 128-bit accesses, 32/tpr rows per step, four steps of loads
+// issued before the first store.
+#include "table.h"
+
+namespace kvhbm {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int UNR = 4;
+
+// modes of a lane's id after phase 1
+constexpr int M_SKIP = -1;   // no output (padding lane / filtered id)
+constexpr int M_ZERO = 0;    // output zeros (absent on predict, blacklisted)
+constexpr int M_COPY = 1;    // row exists
+constexpr int M_FRESH = 2;   // being inserted by another thread of this launch
+constexpr int M_CLAIM = 3;   // this lane inserted the key and must fill the row
+
+// ---------------------------------------------------------------------------
+// KvVariable::FindOrInsert (kv_variable.h:263-380) when INSERT, else
+// KvVariable::FindOrZeros (kv_variable.h:239-254).
+// ---------------------------------------------------------------------------
+template <int VEC, int CPL, bool INSERT>
+__global__ void __launch_bounds__(256)
+gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
+              long long n, float* __restrict__ out, uint32_t today, int tpr) {
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long nwarps = gridDim.x * wpb;
+  const int kpi = 32 / tpr;  // rows per step
+  const int tl = lane & (tpr - 1);
+  const int tq = lane / tpr;
+  const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int dim = t.dim;
+
+  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? ids[i] : 0;
+    int mode = M_SKIP;
+    const float* src = nullptr;
+    float* claim_row = nullptr;
+    long long pos = -1;
+    uint32_t ctl = 0;
+
+    if (valid) {
+      Slot s;
+      mode = M_ZERO;
+      if (INSERT) {
+        bool claimed;
+        pos = find_or_claim(t, key, &s, &claimed);
+        if (pos >= 0) {
+          if (claimed) {
+            ctl = alloc_row(t);
+            claim_row = row_ptr(t, ctl);
+            mode = M_CLAIM;
+          } else {
+            ctl = s.ctl;
+            if (!(ctl & CTL_READY)) ctl = ld_acquire_u32(&t.slots[pos].ctl);
+            if (!(ctl & CTL_READY)) mode = M_FRESH;
+            else if (ctl & CTL_BLACK) mode = M_ZERO;
+            else { mode = M_COPY; src = row_ptr(t, ctl); }
+          }
+        }
+      } else {
+        pos = find_slot(t, key, &s);
+        if (pos >= 0 && (s.ctl & CTL_READY) && !(s.ctl & CTL_BLACK)) {
+          mode = M_COPY;
+          src = row_ptr(t, s.ctl);
+        }
+      }
+    }
+
+    if (INSERT) {
+      // find_func / insert_func frequency bookkeeping, kv_variable.h:323-350,
+      // aggregated over the duplicates inside this warp.
+      const bool has = valid && pos >= 0;
+      const unsigned active = __ballot_sync(FULL, has);
+      if (has) {
+        uint32_t cnt = counts ? saturate_count(counts[i]) : 1u;
+        const unsigned peers = __match_any_sync(active, pos);
+        uint32_t sum = 0;
+        for (unsigned p = peers; p; p &= p - 1)
+          sum += __shfl_sync(peers, cnt, __ffs(p) - 1);
+        if (lane == __ffs(peers) - 1)
+          add_frequency(&t.slots[pos].freq, sum < 0xFFFFu ? sum : 0xFFFFu, today);
+      }
+    }
+
+    // ---- cooperative row movement ----
+    bool my_under = (ctl & CTL_UNDER) != 0;
+    for (int it = 0; it < tpr; it += UNR) {
+      Chunk<VEC> c[UNR][CPL];
+      int m[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        m[u] = M_SKIP;
+        if (it + u < tpr) {
+          const int kl = (it + u) * kpi + tq;
+          m[u] = __shfl_sync(FULL, mode, kl);
+          const float* sp = shfl_ptr(src, kl);
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            if (m[u] == M_COPY && off < dim) c[u][q].load_cg(sp + off);
+            else chunk_zero(c[u][q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (it + u < tpr) {
+          const int kl = (it + u) * kpi + tq;
+          bool big = false;
+          float* op = out + (base + kl) * (long long)dim;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            if (m[u] >= M_ZERO && m[u] <= M_COPY && off < dim) c[u][q].store(op + off);
+            big |= chunk_over_cutoff(c[u][q], DEFAULT_CUTOFF);
+          }
+          if (INSERT) {
+            // UpdateUnderThreshold on a hit (kv_variable.h:329): the owner lane
+            // of each row picks its tile's verdict out of the ballot.
+            const unsigned bal = __ballot_sync(FULL, big);
+            if (lane / kpi == it + u)
+              my_under = ((bal >> ((lane % kpi) * tpr)) & tmask) == 0;
+          }
+        }
+      }
+    }
+    if (INSERT && mode == M_COPY && my_under != ((ctl & CTL_UNDER) != 0)) {
+      if (my_under) atomicOr(&t.slots[pos].ctl, CTL_UNDER);
+      else atomicAnd(&t.slots[pos].ctl, ~CTL_UNDER);
+    }
+
+    if (INSERT) {
+      // New keys (rare after warm-up): the whole warp builds one row at a time.
+      // A lane that lost the claim race to the same key does not wait for the
+      // winner: the initial row is a pure function of the key.
+      unsigned need = __ballot_sync(FULL, mode >= M_FRESH);
+      const int nvec = dim / VEC;
+      while (need) {
+        const int kl = __ffs(need) - 1;
+        need &= need - 1;
+        const long long k = shfl_ll(key, kl);
+        const int m = __shfl_sync(FULL, mode, kl);
+        float* dr = shfl_ptr(claim_row, kl);
+        long long r1, r2;
+        init_rows_of(t, k, &r1, &r2);
+        bool big = false;
+        float* op = out + (base + kl) * (long long)dim;
+        for (int j = lane; j < nvec; j += 32) {
+          Chunk<VEC> c;
+          init_chunk<VEC>(t, r1, r2, j * VEC, c);
+          c.store(op + j * VEC);
+          if (m == M_CLAIM) c.store(dr + j * VEC);
+          big |= chunk_over_cutoff(c, DEFAULT_CUTOFF);
+        }
+        const unsigned bal = __ballot_sync(FULL, big);
+        __syncwarp();
+        if (m == M_CLAIM && lane == kl) {
+          __threadfence();
+          st_release_u32(&t.slots[pos].ctl, CTL_READY | (bal ? 0u : CTL_UNDER) | ctl);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// KvVariable::ScatterUpdate, kv_variable.h:616-734 (unique ids).
+// ---------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float cwise(float l, float r) {
+  // kv_variable_cwise_op.h:19-63; min/max are Eigen's numext::mini/maxi
+  switch (OP) {
+    case 0: return r;
+    case 1: return l + r;
+    case 2: return l - r;
+    case 3: return l * r;
+    case 4: return l / r;
+    case 5: return r < l ? r : l;
+    default: return l < r ? r : l;
+  }
+}
+
+template <int VEC, int CPL, int OP>
+__global__ void __launch_bounds__(256)
+scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __restrict__ upd,
+               long long n, int tpr) {
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long nwarps = gridDim.x * wpb;
+  const int kpi = 32 / tpr;
+  const int tl = lane & (tpr - 1);
+  const int tq = lane / tpr;
+  const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int dim = t.dim;
+
+  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? ids[i] : 0;
+    int mode = M_SKIP;
+    float* row = nullptr;
+    long long pos = -1;
+    uint32_t ctl = 0;
+    if (valid) {
+      Slot s;
+      bool claimed;
+      pos = find_or_claim(t, key, &s, &claimed);
+      if (pos >= 0) {
+        if (claimed) {
+          ctl = alloc_row(t);
+          mode = M_CLAIM;
+          row = row_ptr(t, ctl);
+        } else {
+          ctl = s.ctl;
+          if (ctl & CTL_BLACK) mode = M_SKIP;  // :690 blacklisted keys are skipped
+          else { mode = M_COPY; row = row_ptr(t, ctl); }
+        }
+      }
+    }
+    bool my_under = false;
+    for (int it = 0; it < tpr; ++it) {
+      const int kl = it * kpi + tq;
+      const int m = __shfl_sync(FULL, mode, kl);
+      float* rp = shfl_ptr(row, kl);
+      const long long k = shfl_ll(key, kl);
+      bool big = false;
+      if (m >= M_COPY) {
+        long long r1 = -1, r2 = -1;
+        if (m == M_CLAIM) init_rows_of(t, k, &r1, &r2);
+        const float* up = upd + (base + kl) * (long long)dim;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (off < dim) {
+            Chunk<VEC> cur, u;
+            if (m == M_CLAIM) init_chunk<VEC>(t, r1, r2, off, cur);
+            else cur.load_cg(rp + off);
+            u.load_stream(up + off);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) cur.v[e] = cwise<OP>(cur.v[e], u.v[e]);
+            cur.store(rp + off);
+            big |= chunk_over_cutoff(cur, DEFAULT_CUTOFF);
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(FULL, big);
+      if (lane / kpi == it) my_under = ((bal >> ((lane % kpi) * tpr)) & tmask) == 0;
+    }
+    if (mode == M_CLAIM) {
+      t.slots[pos].freq = 1u << 16;  // EmbeddingValue ctor: freq_val_ = 1
+      __threadfence();
+      t.slots[pos].ctl = CTL_READY | (my_under ? CTL_UNDER : 0u) | ctl;
+    } else if (mode == M_COPY && my_under != ((ctl & CTL_UNDER) != 0)) {
+      t.slots[pos].ctl = my_under ? (ctl | CTL_UNDER) : (ctl & ~CTL_UNDER);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// KvVariable::InsertOrUpdate, kv_variable.h:423-485 (unique ids).
+// ---------------------------------------------------------------------------
+template <int VEC, int CPL>
+__global__ void __launch_bounds__(256)
+insert_kernel(TableView t, const long long* __restrict__ ids, const float* __restrict__ values,
+              long long n, const uint8_t* __restrict__ filter_out,
+              const uint8_t* __restrict__ blacklist, int tpr) {
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long nwarps = gridDim.x * wpb;
+  const int kpi = 32 / tpr;
+  const int tl = lane & (tpr - 1);
+  const int tq = lane / tpr;
+  const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int dim = t.dim;
+
+  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+    const long long i = base + lane;
+    const bool valid = i < n && !(filter_out && filter_out[i]);
+    const long long key = valid ? ids[i] : 0;
+    int mode = M_SKIP;
+    float* row = nullptr;
+    long long pos = -1;
+    uint32_t ctl = 0;
+    bool claimed = false;
+    if (valid) {
+      Slot s;
+      pos = find_or_claim(t, key, &s, &claimed);
+      if (pos >= 0) {
+        ctl = claimed ? alloc_row(t) : s.ctl;
+        if (blacklist && blacklist[i]) {
+          // TableManager::MarkBlacklistUnsafe, table_manager.h:335-357
+          if (claimed) {
+            t.slots[pos].freq = 1u << 16;
+            __threadfence();
+            t.slots[pos].ctl = CTL_READY | CTL_BLACK | ctl;
+          } else if (!(ctl & CTL_BLACK)) {
+            t.slots[pos].ctl = ctl | CTL_BLACK | CTL_UNDER;
+          }
+        } else {
+          mode = M_COPY;
+          row = row_ptr(t, ctl);
+        }
+      }
+    }
+    bool my_under = false;
+    for (int it = 0; it < tpr; ++it) {
+      const int kl = it * kpi + tq;
+      const int m = __shfl_sync(FULL, mode, kl);
+      float* rp = shfl_ptr(row, kl);
+      bool big = false;
+      if (m == M_COPY) {
+        const float* vp = values + (base + kl) * (long long)dim;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (off < dim) {
+            Chunk<VEC> c;
+            c.load_stream(vp + off);
+            c.store(rp + off);
+            big |= chunk_over_cutoff(c, DEFAULT_CUTOFF);
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(FULL, big);
+      if (lane / kpi == it) my_under = ((bal >> ((lane % kpi) * tpr)) & tmask) == 0;
+    }
+    if (mode == M_COPY) {
+      if (claimed) {
+        t.slots[pos].freq = 1u << 16;
+        __threadfence();
+        t.slots[pos].ctl = CTL_READY | (my_under ? CTL_UNDER : 0u) | ctl;
+      } else {
+        // a blacklisted key stays blacklisted and under threshold (:463, :840)
+        const bool under = (ctl & CTL_BLACK) ? true : my_under;
+        const uint32_t nctl = under ? (ctl | CTL_UNDER) : (ctl & ~CTL_UNDER);
+        if (nctl != ctl) t.slots[pos].ctl = nctl;
+      }
+    }
+  }
+}
+
+// KvVariable::GetCount / GetTimeStamp, kv_variable.h:503-561.
+__global__ void get_count_kernel(TableView t, const long long* ids, long long n, int* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    Slot s;
+    out[i] = find_slot(t, ids[i], &s) >= 0 ? (int)freq_count(s.freq) : 0;
+  }
+}
+__global__ void get_timestamp_kernel(TableView t, const long long* ids, long long n,
+                                     uint32_t* out, uint32_t today) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    Slot s;
+    out[i] = find_slot(t, ids[i], &s) >= 0 ? freq_day(s.freq) : today;
+  }
+}
+
+// out[i,:] = src[perm[i],:]  /  out[perm[i],:] = src[i,:]
+template <bool SCATTER>
+__global__ void permute_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm,
+                                    long long n, int dim, float* __restrict__ out) {
+  const long long total = n * (long long)dim;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if ((dim & 3) == 0) {
+    const int d4 = dim >> 2;
+    const long long total4 = n * (long long)d4;
+    for (; e < total4; e += stride) {
+      const long long r = e / d4;
+      const int c = (int)(e - r * d4);
+      const long long p = perm[r];
+      const long long from = SCATTER ? r : p, to = SCATTER ? p : r;
+      reinterpret_cast<float4*>(out)[to * d4 + c] =
+          __ldg(reinterpret_cast<const float4*>(src) + from * d4 + c);
+    }
+  } else {
+    for (; e < total; e += stride) {
+      const long long r = e / dim;
+      const int c = (int)(e - r * dim);
+      const long long p = perm[r];
+      const long long from = SCATTER ? r : p, to = SCATTER ? p : r;
+      out[to * dim + c] = src[from * dim + c];
+    }
+  }
+}
+
+template <int VEC, int CPL>
+int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
+                  float* out, uint16_t today, cudaStream_t st, int tpr) {
+  const int blocks = blocks_for(n, 256, tb->device);
+  const long long* k = reinterpret_cast<const long long*>(ids);
+  if (insert)
+    gather_kernel<VEC, CPL, true><<<blocks, 256, 0, st>>>(tb->view(), k, counts, n, out, today, tpr);
+  else
+    gather_kernel<VEC, CPL, false><<<blocks, 256, 0, st>>>(tb->view(), k, counts, n, out, today, tpr);
+  KV_LAUNCHED();
+  return 0;
+}
+
+template <int VEC, int CPL>
+int launch_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t n,
+                   cudaStream_t st, int tpr) {
+  const int blocks = blocks_for(n, 256, tb->device);
+  const long long* k = reinterpret_cast<const long long*>(ids);
+  TableView v = tb->view();
+  switch (op) {
+    case 0: scatter_kernel<VEC, CPL, 0><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 1: scatter_kernel<VEC, CPL, 1><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 2: scatter_kernel<VEC, CPL, 2><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 3: scatter_kernel<VEC, CPL, 3><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 4: scatter_kernel<VEC, CPL, 4><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 5: scatter_kernel<VEC, CPL, 5><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    case 6: scatter_kernel<VEC, CPL, 6><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    default: return fail(1, "KvVariable: unsupported scatter update operation");
+  }
+  KV_LAUNCHED();
+  return 0;
+}
+
+template <int VEC, int CPL>
+int launch_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
+                  const uint8_t* filter_out, const uint8_t* blacklist, cudaStream_t st, int tpr) {
+  const int blocks = blocks_for(n, 256, tb->device);
+  insert_kernel<VEC, CPL><<<blocks, 256, 0, st>>>(
+      tb->view(), reinterpret_cast<const long long*>(ids), values, n, filter_out, blacklist, tpr);
+  KV_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+// Dispatch on the row geometry.  (VEC, CPL) is one of (4|1) x (1|2|4).
+#define KV_DISPATCH_GEOM(g, CALL)                                   \
+  do {                                                              \
+    if (g.vec == 4) {                                               \
+      if (g.cpl == 1) return CALL(4, 1);                            \
+      if (g.cpl == 2) return CALL(4, 2);                            \
+      return CALL(4, 4);                                            \
+    }                                                               \
+    if (g.cpl == 1) return CALL(1, 1);                              \
+    if (g.cpl == 2) return CALL(1, 2);                              \
+    return CALL(1, 4);                                              \
+  } while (0)
+
+int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
+              float* out, uint16_t today, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (insert) KV_TRY(tb->ensure(n, st));
+  RowGeom g = row_geom(tb->dim);
+  const int cpl = g.cpl == 3 ? 4 : g.cpl;
+  g.cpl = cpl;
+#define CALL(V, C) launch_gather<V, C>(tb, insert, ids, counts, n, out, today, st, g.tpr)
+  KV_DISPATCH_GEOM(g, CALL);
+#undef CALL
+}
+
+int do_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t n,
+               cudaStream_t st) {
+  if (n <= 0) return 0;
+  KV_TRY(tb->ensure(n, st));
+  RowGeom g = row_geom(tb->dim);
+  g.cpl = g.cpl == 3 ? 4 : g.cpl;
+#define CALL(V, C) launch_scatter<V, C>(tb, op, ids, upd, n, st, g.tpr)
+  KV_DISPATCH_GEOM(g, CALL);
+#undef CALL
+}
+
+int do_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
+              const uint8_t* filter_out, const uint8_t* blacklist, cudaStream_t st) {
+  if (n <= 0) return 0;
+  KV_TRY(tb->ensure(n, st));
+  RowGeom g = row_geom(tb->dim);
+  g.cpl = g.cpl == 3 ? 4 : g.cpl;
+#define CALL(V, C) launch_insert<V, C>(tb, ids, values, n, filter_out, blacklist, st, g.tpr)
+  KV_DISPATCH_GEOM(g, CALL);
+#undef CALL
+}
+
+int do_get_count(Table* tb, const int64_t* ids, int64_t n, int32_t* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  get_count_kernel<<<blocks_for(n, 256, tb->device), 256, 0, st>>>(
+      tb->view(), reinterpret_cast<const long long*>(ids), n, out);
+  KV_LAUNCHED();
+  return 0;
+}
+int do_get_timestamp(Table* tb, const int64_t* ids, int64_t n, uint32_t* out, uint16_t today,
+                     cudaStream_t st) {
+  if (n <= 0) return 0;
+  get_timestamp_kernel<<<blocks_for(n, 256, tb->device), 256, 0, st>>>(
+      tb->view(), reinterpret_cast<const long long*>(ids), n, out, today);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_permute_rows(bool scatter, const float* src, const int32_t* perm, int64_t n, int dim,
+                    float* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  const int64_t work = n * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
+  const int blocks = blocks_for(work, 256, dev, 16);
+  if (scatter) permute_rows_kernel<true><<<blocks, 256, 0, st>>>(src, perm, n, dim, out);
+  else permute_rows_kernel<false><<<blocks, 256, 0, st>>>(src, perm, n, dim, out);
+  KV_LAUNCHED();
+  return 0;
+}
+
+}  // namespace kvhbm
