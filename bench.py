@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""KvVariable microbench (BASELINE.json configs[1]): lookup + GroupAdam apply keys/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of B = 65 536 Zipf(1.1) int64 ids on a
+10 M-key, dim-64 table: KvVariableGatherOrInsertV2 on all B ids (forward, not deduped), then
+what TF's optimizer does with the IndexedSlices gradient: Unique + UnsortedSegmentSum, then
+KvVariableGroupSparseApplyAdamV4 on the unique ids.  One JSON line on stdout (rank 0).
+
+N > 1: the table is sharded by key hash, every rank brings its own B ids (weak scaling), ids /
+rows / gradients cross NVLink by all-to-all (tfplus_b200/sharded.py).
+
+--impl reference times the reference's CPU algorithm (the oracle port: TensorFlow and the
+reference's Bazel build are not available) on the host cores, same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+KEYS = 10_000_000
+DIM = 64
+BATCH = 65536
+INIT_ROWS = 10000
+ZIPF_S = 1.1
+PERM_A = 7368787            # rank -> id: (rank * A) mod KEYS, A coprime to 10^7
+N_BATCHES = 16              # rotating input batches (16 x 17.3 MB = 277 MB > 126 MB L2)
+HP = dict(lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, l1=1e-5, l2=1e-5, l21=1e-5)
+TODAY = 20000
+METRIC = "KvVariable lookup+GroupAdam apply keys/s"
+UNIT = "keys/s"
+
+
+# ----------------------------------------------------------------------------- workload
+class ZipfSampler:
+  """Inverse-CDF Zipf(s) over ranks 1..n, numpy PCG64."""
+
+  def __init__(self, n, s, seed):
+    w = np.arange(1, n + 1, dtype=np.float64) ** (-s)
+    self.cdf = np.cumsum(w)
+    self.cdf /= self.cdf[-1]
+    self.n = n
+    self.rng = np.random.Generator(np.random.PCG64(seed))
+
+  def ids(self, b, offset=0):
+    r = np.searchsorted(self.cdf, self.rng.random(b)).astype(np.int64)
+    return ((r + 1) * PERM_A) % self.n + offset
+
+
+def make_batches(n_batches, keys, batch, dim, seed_ids=2024, seed_grad=7, offset=0):
+  z = ZipfSampler(keys, ZIPF_S, seed_ids)
+  g = np.random.Generator(np.random.PCG64(seed_grad))
+  ids = [z.ids(batch, offset) for _ in range(n_batches)]
+  grads = [g.standard_normal((batch, dim), dtype=np.float32) for _ in range(n_batches)]
+  return ids, grads
+
+
+def init_table(dim):
+  return np.random.Generator(np.random.PCG64(1234)).normal(0, 0.05, (INIT_ROWS, dim)).astype(
+      np.float32)
+
+
+def algorithmic_bytes(b, u, d):
+  """SURVEY.md 8(d) / BASELINE.md 3 per-stage algorithmic bytes."""
+  return {
+      "gather": (8 + 12 + 4 + 4 * d + 4 * d) * b,
+      "unique": 8 * b + 8 * u + 4 * b,
+      "segment_sum": b * (4 * d + 4) + 4 * d * u,
+      "apply": (8 + 2 * 12 + 4 * d + 2 * 4 * d + 2 * 3 * 4 * d) * u,
+  }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+  """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz = [], set(), None
+    self._stop = threading.Event()
+    self._t = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:
+      self.nv = None
+
+  def _once(self):
+    nv = self.nv
+    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+    names = {
+        "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+        "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+        "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+        "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+    }
+    for k, bit in names.items():
+      if r & bit:
+        self.reasons.add(k)
+
+  def start(self):
+    if not self.nv:
+      return
+    def run():
+      while not self._stop.is_set():
+        try:
+          self._once()
+        except Exception:
+          return
+        time.sleep(0.002)
+    self._t = threading.Thread(target=run, daemon=True)
+    self._t.start()
+
+  def stop(self):
+    if not self.nv:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+    try:
+      self._once()
+    except Exception:
+      pass
+    self._stop.set()
+    if self._t:
+      self._t.join()
+    med = float(np.median(self.samples)) if self.samples else None
+    return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+            "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_cpu(steps, warmup, keys, batch, dim, threads=None, quiet=False):
+  """The reference algorithm on the host cores (oracle port).  Returns (keys/s, info)."""
+  from oracle import binding as ob
+  threads = threads or os.cpu_count() or 1
+  ob.set_threads(threads)
+  var = ob.OracleTable(dim, 0, seed=1)
+  slot = ob.OracleTable(3 * dim, 0, seed=1)
+  var.set_init_table(init_table(dim))
+  slot.set_init_table(np.zeros((INIT_ROWS, 3 * dim), np.float32))
+  for s in range(0, keys, 1 << 20):
+    ids = np.arange(s, min(keys, s + (1 << 20)), dtype=np.int64)
+    var.gather_or_insert(ids, today=TODAY)
+    slot.gather_or_insert(ids, today=TODAY)
+  nb = min(N_BATCHES, steps + warmup)
+  ids_l, grads_l = make_batches(nb, keys, batch, dim)
+  b1p, b2p = HP["beta1"], HP["beta2"]
+  t0 = None
+  for i in range(warmup + steps):
+    if i == warmup:
+      t0 = time.perf_counter()
+    ids, g = ids_l[i % nb], grads_l[i % nb]
+    var.gather_or_insert(ids, today=TODAY)
+    u, idx = ob.unique(ids)                      # TF Unique (single-threaded CPU kernel)
+    gs = ob.segment_sum(g, idx, u.size)          # TF UnsortedSegmentSum
+    ob.apply_group_adam_v4(var, slot, u, gs, HP["lr"], b1p, b2p, HP["beta1"], HP["beta2"],
+                           HP["epsilon"], HP["l1"], HP["l2"], HP["l21"], today=TODAY)
+    b1p *= HP["beta1"]
+    b2p *= HP["beta2"]
+  dt = time.perf_counter() - t0
+  return batch * steps / dt, {"seconds": dt, "threads": threads}
+
+
+def main_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return 0
+  steps = max(1, args.steps)
+  cores = os.cpu_count() or 1
+  val, info = run_cpu(steps, args.warmup, args.keys, args.batch, args.dim, cores)
+  sample = "%d-key table, %d timed steps of B=%d (whole workload, no subsampling)" % (
+      args.keys, steps, args.batch)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+      "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic", "config": workload_config(args, 1),
+      "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+  return 0
+
+
+def workload_config(args, n_gpus):
+  return {
+      "workload": "KvVariable microbench: %d-key int64 table per GPU x %d GPU(s), dim %d, batch %d "
+                  "Zipf(%.1f) ids per GPU, gather_or_insert + unique + segment_sum + "
+                  "GroupAdam v4 apply (lr 1e-3, l1=l2=l21=1e-5)" % (
+                      args.keys, n_gpus, args.dim, args.batch, ZIPF_S),
+      "keys": args.keys * n_gpus, "dim": args.dim, "batch_per_gpu": args.batch,
+      "global_batch": args.batch * n_gpus,
+      "parallelism": "single GPU" if n_gpus == 1 else "key-hash sharding x%d" % n_gpus,
+      "l2": "table working set %.1f GB >> 126 MB L2; %d rotating input batches (%.0f MB)" % (
+          args.keys * args.dim * 4 * 4 / 1e9, N_BATCHES,
+          N_BATCHES * args.batch * (8 + 4 * args.dim) / 1e6),
+  }
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main_ours(args):
+  import torch
+  import torch.distributed as dist
+  from tfplus_b200 import _lib, ops
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
+                     "use --impl reference for the CPU arm")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  ops.set_today(TODAY)
+  K, W = max(1, args.steps), max(3, args.warmup)
+  keys, B, D = args.keys, args.batch, args.dim
+
+  if world > 1:
+    from tfplus_b200 import sharded
+    stepper = sharded.ShardedStepper(keys, D, B, HP, dev, rank, world)
+  else:
+    stepper = LocalStepper(keys, D, B, dev)
+  stepper.populate()
+
+  nb = N_BATCHES
+  ids_np, grads_np = make_batches(nb, keys * world, B, D, seed_ids=2024 + rank,
+                                  seed_grad=7 + rank)
+  ids_d = [torch.from_numpy(x).to(dev) for x in ids_np]
+  grads_d = [torch.from_numpy(x).to(dev) for x in grads_np]
+  u_meas = float(np.mean([np.unique(x).size for x in ids_np]))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- warm-up + timed region (inputs resident in HBM) ----
+  stepper.prepare(ids_d, grads_d)
+  for i in range(W):
+    stepper.step(i)
+  barrier()
+  clocks = ClockSampler(local_rank)
+  clocks.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(K):
+    stepper.step(i)
+  e1.record()
+  barrier()
+  launches = K * stepper.launches_per_step   # graph replays: counted at capture time
+  ms = e0.elapsed_time(e1)
+  clk = clocks.stop()
+  if world > 1:
+    tt = torch.tensor([ms], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+  value = B * world * K / (ms * 1e-3)
+
+  # ---- per-stage device times (same steps, events between the stages) ----
+  stage_ms = stepper.stage_times(K)
+
+  # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
+  ids_h = [torch.from_numpy(x).pin_memory() for x in ids_np]
+  grads_h = [torch.from_numpy(x).pin_memory() for x in grads_np]
+  rows_h = torch.empty((B, D), dtype=torch.float32).pin_memory()
+  stepper.prepare_host(ids_h, grads_h, rows_h)
+  for i in range(3):
+    stepper.step_host(i)
+  barrier()
+  f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  f0.record()
+  for i in range(K):
+    stepper.step_host(i)
+  f1.record()
+  barrier()
+  e2e_ms = f0.elapsed_time(f1)
+  if world > 1:
+    tt = torch.tensor([e2e_ms], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tt.item())
+  e2e_val = B * world * K / (e2e_ms * 1e-3)
+
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+      pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    ab = algorithmic_bytes(B, u_meas, D)
+    kern = {}
+    for name, t_ms in stage_ms.items():
+      if name in ab and t_ms > 0:
+        kern[name] = {"ms": t_ms, "algorithmic_bytes": ab[name],
+                      "achieved_gbs": ab[name] / (t_ms * 1e-3) / 1e9,
+                      "frac": ab[name] / (t_ms * 1e-3) / 1e9 / peak}
+    top = max((k for k in kern), key=lambda k: kern[k]["ms"]) if kern else None
+    roof = None
+    if top:
+      roof = {"bound": "hbm", "kernel": top, "achieved": kern[top]["achieved_gbs"], "peak": peak,
+              "unit": "GB/s", "frac": kern[top]["frac"], "traffic": TRAFFIC.get(top),
+              "peak_source": peak_src, "stages": kern,
+              "step_algorithmic_bytes": sum(ab.values()),
+              "step_frac_of_peak": sum(ab.values()) / (ms / K * 1e-3) / 1e9 / peak,
+              "step_frac_of_8TBs": sum(ab.values()) / (ms / K * 1e-3) / 1e9 / 8000.0}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "unique_per_step": u_meas, "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": UNIT,
+                "h2d_bytes_per_step": int(B * 8 + B * D * 4),
+                "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K},
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu:
+      cores = os.cpu_count() or 1
+      cs = max(3, min(20, K))
+      v, info = run_cpu(cs, 2, keys, B, D, cores)
+      line["cpu_baseline"] = {
+          "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": "same workload (%d-key table), %d timed steps of B=%d after 2 warm-up, "
+                    "oracle port of the reference algorithm, %d threads" % (keys, cs, B, cores)}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+  return 0
+
+
+# dram bytes per launch from the committed ncu --set full captures (profiles/), or None
+TRAFFIC = {}
+
+
+class LocalStepper:
+  """One GPU: var + m_v_linear tables and the four-stage step.
+
+  The optimizer's scalar inputs live in device memory (`hp`, as TF would hand them to a GPU
+  kernel) and beta^t is advanced on the device after every apply (TF Adam's `_finish`), so a
+  whole step is capturable: the timed loops replay one CUDA graph per rotating batch instead of
+  paying ~10 host launches per 30 us step.
+  """
+
+  STAGES = ["gather", "unique", "segment_sum", "apply"]
+
+  def __init__(self, keys, dim, batch, dev):
+    import torch
+    from tfplus_b200 import ops
+    self.torch, self.ops = torch, ops
+    self.keys, self.dim, self.batch, self.dev = keys, dim, batch, dev
+    self.var = ops.kv_variable(value_shape=[dim], device=dev, capacity_hint=keys + batch, seed=1)
+    self.slot = ops.kv_variable(value_shape=[3 * dim], device=dev, capacity_hint=keys + batch,
+                                seed=1)
+    ops.init_kv_variable_v2(self.var, torch.from_numpy(init_table(dim)).to(dev))
+    ops.init_kv_variable_v2(self.slot, torch.zeros(INIT_ROWS, 3 * dim, device=dev))
+    self.hp = torch.tensor([HP["lr"], HP["beta1"], HP["beta2"], HP["beta1"], HP["beta2"],
+                            HP["epsilon"], HP["l1"], HP["l2"], HP["l21"]], dtype=torch.float32,
+                           device=dev)
+    self.betas = torch.tensor([HP["beta1"], HP["beta2"]], dtype=torch.float32, device=dev)
+    self.graphs = {}
+
+  def populate(self):
+    torch, ops = self.torch, self.ops
+    for s in range(0, self.keys, 1 << 20):
+      ids = torch.arange(s, min(self.keys, s + (1 << 20)), dtype=torch.int64, device=self.dev)
+      ops.kv_variable_gather_or_insert_v2(self.var, ids)
+      ops.kv_variable_gather_or_insert_v2(self.slot, ids)
+    torch.cuda.synchronize()
+
+  # ---- the step, stage by stage (eager; also what gets captured) ----
+  def new_buffers(self):
+    t, B, D, dev = self.torch, self.batch, self.dim, self.dev
+    return {"rows": t.empty((B, D), dtype=t.float32, device=dev),
+            "uniq": t.empty(B, dtype=t.int64, device=dev),
+            "idx": t.empty(B, dtype=t.int32, device=dev),
+            "num": t.zeros(1, dtype=t.int32, device=dev),
+            "gsum": t.empty((B, D), dtype=t.float32, device=dev)}
+
+  def stage(self, name, ids, grad, buf):
+    ops, lib, C = self.ops, self.ops._lib.load(), self.ops.check
+    st = self.torch.cuda.current_stream(self.dev).cuda_stream
+    if name == "gather":
+      ops.kv_variable_gather_or_insert_v2(self.var, ids, out=buf["rows"])
+    elif name == "unique":
+      ws = ops.Workspace.get(self.dev)
+      C(lib.kv_unique(ws.ptr, ids.data_ptr(), ids.numel(), buf["uniq"].data_ptr(),
+                      buf["idx"].data_ptr(), None, buf["num"].data_ptr(), st))
+    elif name == "segment_sum":
+      ops.unsorted_segment_sum(grad, buf["idx"], buf["num"], out=buf["gsum"])
+    elif name == "apply":
+      ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, buf["gsum"], buf["uniq"],
+                                                     self.hp, num_indices=buf["num"])
+      self.hp[1:3].mul_(self.betas)   # beta1_power *= beta1, beta2_power *= beta2
+
+  def step_eager(self, ids, grad, buf):
+    for name in self.STAGES:
+      self.stage(name, ids, grad, buf)
+    return buf["rows"]
+
+  def _capture(self, fn):
+    torch = self.torch
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      fn()
+    return g
+
+  def prepare(self, ids_d, grads_d):
+    """Warm every batch once eagerly (sizes the workspace, no allocation later), then capture
+    one full-step graph and four single-stage graphs per batch."""
+    self.ids_d, self.grads_d = ids_d, grads_d
+    self.bufs = [self.new_buffers() for _ in ids_d]
+    l0 = self.ops._lib.launch_count()
+    for ids, grad, buf in zip(ids_d, grads_d, self.bufs):
+      self.step_eager(ids, grad, buf)
+    # kernels of this library per step (+1: torch's in-place multiply that advances beta^t)
+    self.launches_per_step = (self.ops._lib.launch_count() - l0) // len(ids_d)
+    self.torch.cuda.synchronize()
+    # captured work may not grow the tables: make the room now (also refreshes the exact counts)
+    self.ops.kv_variable_reserve(self.var, 2 * self.batch)
+    self.ops.kv_variable_reserve(self.slot, 2 * self.batch)
+    self.full = [self._capture(lambda i=i: self.step_eager(ids_d[i], grads_d[i], self.bufs[i]))
+                 for i in range(len(ids_d))]
+    self.stage_graphs = {
+        n: [self._capture(lambda i=i, n=n: self.stage(n, ids_d[i], grads_d[i], self.bufs[i]))
+            for i in range(len(ids_d))] for n in self.STAGES}
+    self.torch.cuda.synchronize()
+
+  def step(self, i):
+    self.full[i % len(self.full)].replay()
+
+  def stage_times(self, steps):
+    """Average device time of each stage: K back-to-back replays of that stage's graph over the
+    rotating batches, bracketed by CUDA events on the launching stream."""
+    torch = self.torch
+    out = {}
+    for n in self.STAGES:
+      gs = self.stage_graphs[n]
+      for i in range(3):
+        gs[i % len(gs)].replay()
+      torch.cuda.synchronize()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for i in range(steps):
+        gs[i % len(gs)].replay()
+      b.record()
+      torch.cuda.synchronize()
+      out[n] = a.elapsed_time(b) / steps
+    return out
+
+  # ---- end to end: pinned host buffers in, pinned host rows out ----
+  def prepare_host(self, ids_h, grads_h, rows_h):
+    t = self.torch
+    self.h_ids = t.empty(self.batch, dtype=t.int64, device=self.dev)
+    self.h_grad = t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+    self.h_buf = self.new_buffers()
+
+    def one(i):
+      self.h_ids.copy_(ids_h[i], non_blocking=True)
+      self.h_grad.copy_(grads_h[i], non_blocking=True)
+      rows = self.step_eager(self.h_ids, self.h_grad, self.h_buf)
+      rows_h.copy_(rows, non_blocking=True)
+
+    one(0)
+    t.cuda.synchronize()
+    self.e2e = [self._capture(lambda i=i: one(i)) for i in range(len(ids_h))]
+
+  def step_host(self, i):
+    self.e2e[i % len(self.e2e)].replay()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--warmup", type=int, default=20)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--keys", type=int, default=KEYS)
+  ap.add_argument("--batch", type=int, default=BATCH)
+  ap.add_argument("--dim", type=int, default=DIM)
+  ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    return main_reference(args)
+  return main_ours(args)
+
+
+if __name__ == "__main__":
+  sys.exit(main())

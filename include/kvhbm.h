@@ -145,6 +145,30 @@ int kv_apply_adam(kv_table* var, kv_table* m_v, const int64_t* d_ids,
                   float beta1, float beta2, float epsilon, float beta1_power,
                   float beta2_power, uint16_t today, kv_stream stream);
 
+/* The same four ops with their scalar inputs left in DEVICE memory (a TF GPU
+ * kernel sees lr, beta1_power, ... as device tensors unless they are pinned
+ * to HostMemory).  d_hp holds the op's scalar inputs in op order:
+ *   adagrad [lr]; group_adam_v4 [lr, beta1_power, beta2_power, beta1, beta2,
+ *   epsilon, l1, l2, l21]; sparse_group_ftrl [lr, l1, l2, l21, l2_shrinkage,
+ *   lr_power]; adam [lr, beta1, beta2, epsilon, beta1_power, beta2_power].
+ * Nothing is read back, so a whole step can be captured in a CUDA graph and
+ * replayed while beta^t advances on the device; the sign checks of the host
+ * variants are skipped. */
+int kv_apply_adagrad_dev(kv_table* var, kv_table* accum, const int64_t* d_ids,
+                         const float* d_grad, int64_t n, const int32_t* d_n,
+                         const float* d_hp, int update_slots, uint16_t today,
+                         kv_stream stream);
+int kv_apply_group_adam_v4_dev(kv_table* var, kv_table* m_v_linear, const int64_t* d_ids,
+                               const float* d_grad, int64_t n, const int32_t* d_n,
+                               const float* d_hp, uint16_t today, kv_stream stream);
+int kv_apply_sparse_group_ftrl_dev(kv_table* var, kv_table* accum, kv_table* linear,
+                                   const int64_t* d_ids, const float* d_grad, int64_t n,
+                                   const int32_t* d_n, const float* d_hp, uint16_t today,
+                                   kv_stream stream);
+int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids,
+                      const float* d_grad, int64_t n, const int32_t* d_n,
+                      const float* d_hp, uint16_t today, kv_stream stream);
+
 /* ---- dedup (stock TF ops on the path; TF 2.13 Unique / UnsortedSegmentSum) */
 
 int kv_workspace_create(kv_workspace** out);

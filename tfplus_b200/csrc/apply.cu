@@ -29,6 +29,56 @@ struct ApplyParams {
   int fast_sqrt;    // lr_power == -0.5
 };
 
+// Scalars every row needs, derived from the op's hyper-parameter inputs exactly as the
+// reference derives them.  One __host__ __device__ body so that the host path (scalars
+// passed by value, as TF HostMemory inputs) and the device path (scalars read from HBM, so
+// that a step can be captured in a CUDA graph and replayed while beta^t advances) round
+// identically.  `hp` layout per optimizer = the op's scalar inputs in op order:
+//   adagrad     [lr]
+//   group adam  [lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21]
+//   ftrl        [lr, l1, l2, l21, l2_shrinkage, lr_power]
+//   adam        [lr, beta1, beta2, epsilon, beta1_power, beta2_power]
+template <int KIND>
+__host__ __device__ __forceinline__ ApplyParams derive_params(const float* hp, int dim,
+                                                              int update_slots) {
+  ApplyParams p;
+  p.lr = hp[0];
+  p.beta1 = p.beta2 = p.one_minus_beta1 = p.one_minus_beta2 = p.epsilon = 0.f;
+  p.alpha = p.l1 = p.l2x2 = p.l21_norm = p.shrink2 = p.neg_lr_power = 0.f;
+  p.later_step = 0;
+  p.update_slots = update_slots;
+  p.fast_sqrt = 0;
+  if (KIND == K_GROUP_ADAM) {
+    const float lr = hp[0], b1p = hp[1], b2p = hp[2];
+    p.beta1 = hp[3];
+    p.beta2 = hp[4];
+    p.epsilon = hp[5];
+    p.one_minus_beta1 = 1.0f - p.beta1;
+    p.one_minus_beta2 = 1.0f - p.beta2;
+    const float l1s = hp[6] * lr, l2s = hp[7] * lr, l21s = hp[8] * lr;  // :7111-7113
+    p.l1 = l1s;
+    p.l2x2 = 2.0f * l2s;
+    p.alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);          // :7117-7119
+    p.l21_norm = l21s * sqrtf(static_cast<float>(dim));       // :7120
+    p.later_step = p.beta1 > b1p;                             // :7171
+  } else if (KIND == K_FTRL) {
+    p.l1 = hp[1];
+    p.l2x2 = 2.0f * hp[2];
+    p.l21_norm = hp[3] * sqrtf(static_cast<float>(dim));      // :728
+    p.shrink2 = 2.0f * hp[4];
+    p.neg_lr_power = -hp[5];
+    p.fast_sqrt = hp[5] == -0.5f;                             // :715
+  } else if (KIND == K_ADAM) {
+    p.beta1 = hp[1];
+    p.beta2 = hp[2];
+    p.epsilon = hp[3];
+    p.one_minus_beta1 = 1.0f - p.beta1;
+    p.one_minus_beta2 = 1.0f - p.beta2;
+    p.alpha = (hp[0] * sqrtf(1.0f - hp[5])) / (1.0f - hp[4]);  // adam.py:147-148
+  }
+  return p;
+}
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -78,7 +128,8 @@ template <int VEC, int CPL, int UNR, int KIND>
 __global__ void __launch_bounds__(128)
 apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restrict__ ids,
              const float* __restrict__ grad, long long n, const int* __restrict__ d_n,
-             ApplyParams p, uint32_t today, int tpr) {
+             ApplyParams p, const float* __restrict__ d_hp, uint32_t today, int tpr) {
+  if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p.update_slots);
   constexpr int PARTS = Kind<KIND>::PARTS;
   constexpr bool TWO = Kind<KIND>::TWO;
   const int lane = threadIdx.x & 31;
@@ -350,29 +401,32 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
 
 template <int VEC, int CPL, int KIND>
 int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
-                 int64_t n, const int32_t* d_n, const ApplyParams& p, uint16_t today,
-                 cudaStream_t st, int tpr) {
+                 int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
+                 uint16_t today, cudaStream_t st, int tpr) {
   constexpr int UNR = CPL == 1 ? 4 : (CPL == 2 ? 2 : 1);
   const int blocks = blocks_for(n, 128, var->device, 16);
   TableView vb = sb ? sb->view() : sa->view();
   apply_kernel<VEC, CPL, UNR, KIND><<<blocks, 128, 0, st>>>(
       var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,
-      today, tpr);
+      d_hp, today, tpr);
   KV_LAUNCHED();
   return 0;
 }
 
 template <int KIND>
 int dispatch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
-                   int64_t n, const int32_t* d_n, const ApplyParams& p, uint16_t today,
-                   cudaStream_t st) {
+                   int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
+                   uint16_t today, cudaStream_t st) {
   if (n <= 0) return 0;
   KV_TRY(var->ensure(n, st));
   KV_TRY(sa->ensure(n, st));
   if (sb) KV_TRY(sb->ensure(n, st));
   RowGeom g = row_geom(var->dim);
+  if (g.cpl > 4)
+    return fail(3, "fused apply: embedding dim " + std::to_string(var->dim) +
+                       " not supported (max 512 when a multiple of 4, else 128)");
   const int cpl = g.cpl == 3 ? 4 : g.cpl;
-#define CALL(V, C) launch_apply<V, C, KIND>(var, sa, sb, ids, grad, n, d_n, p, today, st, g.tpr)
+#define CALL(V, C) launch_apply<V, C, KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st, g.tpr)
   if (g.vec == 4) {
     if (cpl == 1) return CALL(4, 1);
     if (cpl == 2) return CALL(4, 2);
@@ -392,91 +446,74 @@ int check_initialized(const Table* t, const char* what) {
 
 }  // namespace
 
+// Host-side entry points.  `hp` holds the op's scalar inputs on the host (validated as the
+// reference validates them) or, when `d_hp` is given, in device memory (not validated: reading
+// them back would need a stream synchronisation).
+template <int KIND>
+static int apply_common(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
+                        int64_t n, const int32_t* d_n, const float* hp, const float* d_hp,
+                        int update_slots, uint16_t today, cudaStream_t st) {
+  ApplyParams p{};
+  if (d_hp == nullptr) p = derive_params<KIND>(hp, var->dim, update_slots);
+  p.update_slots = update_slots;
+  return dispatch_apply<KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st);
+}
+
 int do_apply_adagrad(Table* var, Table* accum, const int64_t* ids, const float* grad, int64_t n,
-                     const int32_t* d_n, float lr, int update_slots, uint16_t today,
-                     cudaStream_t st) {
+                     const int32_t* d_n, const float* hp, const float* d_hp, int update_slots,
+                     uint16_t today, cudaStream_t st) {
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(accum, "accum"));
-  if (accum->dim != var->dim)
-    return fail(1, "var and accum do not have the same shape");
-  ApplyParams p{};
-  p.lr = lr;
-  p.update_slots = update_slots;
-  return dispatch_apply<K_ADAGRAD>(var, accum, nullptr, ids, grad, n, d_n, p, today, st);
+  if (accum->dim != var->dim) return fail(1, "var and accum do not have the same shape");
+  return apply_common<K_ADAGRAD>(var, accum, nullptr, ids, grad, n, d_n, hp, d_hp, update_slots,
+                                 today, st);
 }
 
 int do_apply_group_adam_v4(Table* var, Table* mvl, const int64_t* ids, const float* grad,
-                           int64_t n, const int32_t* d_n, float lr, float beta1_power,
-                           float beta2_power, float beta1, float beta2, float epsilon, float l1,
-                           float l2, float l21, uint16_t today, cudaStream_t st) {
+                           int64_t n, const int32_t* d_n, const float* hp, const float* d_hp,
+                           uint16_t today, cudaStream_t st) {
   // argument checks of training_ops.cc:7001-7103
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(mvl, "m_v_linear"));
-  if (!(lr > 0.f)) return fail(1, "lr is not a positive scalar");
-  if (!(l1 >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
-  if (!(l2 >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
-  if (!(l21 >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
+  if (d_hp == nullptr) {
+    if (!(hp[0] > 0.f)) return fail(1, "lr is not a positive scalar");
+    if (!(hp[6] >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
+    if (!(hp[7] >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
+    if (!(hp[8] >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
+  }
   if (mvl->dim != 3 * var->dim)
     return fail(1, "kv_variable and linear do not have the same shape");
-  ApplyParams p{};
-  p.lr = lr;
-  p.beta1 = beta1;
-  p.beta2 = beta2;
-  p.one_minus_beta1 = 1.0f - beta1;
-  p.one_minus_beta2 = 1.0f - beta2;
-  p.epsilon = epsilon;
-  const float l1s = l1 * lr, l2s = l2 * lr, l21s = l21 * lr;  // :7111-7113
-  p.l1 = l1s;
-  p.l2x2 = 2.0f * l2s;
-  p.alpha = lr * sqrtf(1.0f - beta2_power) / (1.0f - beta1_power);  // :7117-7119
-  p.l21_norm = l21s * sqrtf(static_cast<float>(var->dim));           // :7120
-  p.later_step = beta1 > beta1_power;                                 // :7171
-  return dispatch_apply<K_GROUP_ADAM>(var, mvl, nullptr, ids, grad, n, d_n, p, today, st);
+  return apply_common<K_GROUP_ADAM>(var, mvl, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st);
 }
 
 int do_apply_sparse_group_ftrl(Table* var, Table* accum, Table* linear, const int64_t* ids,
-                               const float* grad, int64_t n, const int32_t* d_n, float lr,
-                               float l1, float l2, float l21, float l2_shrinkage, float lr_power,
-                               uint16_t today, cudaStream_t st) {
+                               const float* grad, int64_t n, const int32_t* d_n, const float* hp,
+                               const float* d_hp, uint16_t today, cudaStream_t st) {
   // argument checks of training_ops.cc:560-659
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(accum, "accum"));
   KV_TRY(check_initialized(linear, "linear"));
-  if (!(lr > 0.f)) return fail(1, "lr is not a positive scalar");
-  if (!(l1 >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
-  if (!(l2 >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
-  if (!(l21 >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
-  if (!(l2_shrinkage >= 0.f))
-    return fail(1, "l2 shrinkage regularization strength is not a non-negative scalar");
-  if (!(lr_power <= 0.f)) return fail(1, "lr_power is not a non-positive scalar");
+  if (d_hp == nullptr) {
+    if (!(hp[0] > 0.f)) return fail(1, "lr is not a positive scalar");
+    if (!(hp[1] >= 0.f)) return fail(1, "l1 regularization strength is not a non-negative scalar");
+    if (!(hp[2] >= 0.f)) return fail(1, "l2 regularization strength is not a non-negative scalar");
+    if (!(hp[3] >= 0.f)) return fail(1, "l21 regularization strength is not a non-negative scalar");
+    if (!(hp[4] >= 0.f))
+      return fail(1, "l2 shrinkage regularization strength is not a non-negative scalar");
+    if (!(hp[5] <= 0.f)) return fail(1, "lr_power is not a non-positive scalar");
+  }
   if (accum->dim != var->dim) return fail(1, "kv_varaible and accum do not have the same shape");
   if (linear->dim != var->dim) return fail(1, "kv_variable and linear do not have the same shape");
-  ApplyParams p{};
-  p.lr = lr;
-  p.l1 = l1;
-  p.l2x2 = 2.0f * l2;
-  p.l21_norm = l21 * sqrtf(static_cast<float>(var->dim));
-  p.shrink2 = 2.0f * l2_shrinkage;
-  p.neg_lr_power = -lr_power;
-  p.fast_sqrt = lr_power == -0.5f;
-  return dispatch_apply<K_FTRL>(var, accum, linear, ids, grad, n, d_n, p, today, st);
+  return apply_common<K_FTRL>(var, accum, linear, ids, grad, n, d_n, hp, d_hp, 1, today, st);
 }
 
 int do_apply_adam(Table* var, Table* mv, const int64_t* ids, const float* grad, int64_t n,
-                  const int32_t* d_n, float lr, float beta1, float beta2, float epsilon,
-                  float beta1_power, float beta2_power, uint16_t today, cudaStream_t st) {
+                  const int32_t* d_n, const float* hp, const float* d_hp, uint16_t today,
+                  cudaStream_t st) {
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(mv, "m_v"));
   if (mv->dim != 2 * var->dim) return fail(1, "m_v slot must have dim 2 * dim(var)");
-  ApplyParams p{};
-  p.lr = lr;
-  p.beta1 = beta1;
-  p.beta2 = beta2;
-  p.one_minus_beta1 = 1.0f - beta1;
-  p.one_minus_beta2 = 1.0f - beta2;
-  p.epsilon = epsilon;
-  p.alpha = (lr * sqrtf(1.0f - beta2_power)) / (1.0f - beta1_power);  // adam.py:147-148
-  return dispatch_apply<K_ADAM>(var, mv, nullptr, ids, grad, n, d_n, p, today, st);
+  return apply_common<K_ADAM>(var, mv, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st);
 }
 
 }  // namespace kvhbm

@@ -21,16 +21,15 @@ int do_get_count(Table*, const int64_t*, int64_t, int32_t*, cudaStream_t);
 int do_get_timestamp(Table*, const int64_t*, int64_t, uint32_t*, uint16_t, cudaStream_t);
 int do_permute_rows(bool scatter, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
 
-int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*, float,
-                     int, uint16_t, cudaStream_t);
+int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
+                     const float* hp, const float* d_hp, int, uint16_t, cudaStream_t);
 int do_apply_group_adam_v4(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
-                           float, float, float, float, float, float, float, float, float, uint16_t,
-                           cudaStream_t);
+                           const float* hp, const float* d_hp, uint16_t, cudaStream_t);
 int do_apply_sparse_group_ftrl(Table*, Table*, Table*, const int64_t*, const float*, int64_t,
-                               const int32_t*, float, float, float, float, float, float, uint16_t,
+                               const int32_t*, const float* hp, const float* d_hp, uint16_t,
                                cudaStream_t);
-int do_apply_adam(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*, float,
-                  float, float, float, float, float, uint16_t, cudaStream_t);
+int do_apply_adam(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
+                  const float* hp, const float* d_hp, uint16_t, cudaStream_t);
 
 int do_unique(Workspace*, const int64_t*, int64_t, int64_t*, int32_t*, int32_t*, int32_t*,
               cudaStream_t);
@@ -132,7 +131,7 @@ int kv_set_seed(kv_table* t, uint64_t seed) {
 int kv_reserve(kv_table* t, int64_t n_keys, kv_stream stream) {
   KV_ENTER(t);
   Table& tb = t->t;
-  KV_TRY(tb.ensure(n_keys, S(stream)));
+  KV_TRY(tb.ensure(n_keys, S(stream), /*exact=*/true));
   // ensure() books the keys as used; a reservation does not insert anything
   tb.used_ub -= (uint64_t)n_keys;
   tb.rows_ub -= (uint64_t)n_keys;
@@ -235,8 +234,9 @@ int kv_apply_adagrad(kv_table* var, kv_table* accum, const int64_t* d_ids, const
                      kv_stream stream) {
   MultiGuard g(var, accum, nullptr);
   if (g.rc) return g.rc;
-  return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, lr, update_slots, today,
-                          S(stream));
+  const float hp[1] = {lr};
+  return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, hp, nullptr, update_slots,
+                          today, S(stream));
 }
 int kv_apply_group_adam_v4(kv_table* var, kv_table* mvl, const int64_t* d_ids,
                            const float* d_grad, int64_t n, const int32_t* d_n, float lr,
@@ -245,8 +245,9 @@ int kv_apply_group_adam_v4(kv_table* var, kv_table* mvl, const int64_t* d_ids,
                            kv_stream stream) {
   MultiGuard g(var, mvl, nullptr);
   if (g.rc) return g.rc;
-  return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, lr, beta1_power,
-                                beta2_power, beta1, beta2, epsilon, l1, l2, l21, today, S(stream));
+  const float hp[9] = {lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21};
+  return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, hp, nullptr, today,
+                                S(stream));
 }
 int kv_apply_sparse_group_ftrl(kv_table* var, kv_table* accum, kv_table* linear,
                                const int64_t* d_ids, const float* d_grad, int64_t n,
@@ -255,16 +256,55 @@ int kv_apply_sparse_group_ftrl(kv_table* var, kv_table* accum, kv_table* linear,
                                kv_stream stream) {
   MultiGuard g(var, accum, linear);
   if (g.rc) return g.rc;
-  return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, lr, l1,
-                                    l2, l21, l2_shrinkage, lr_power, today, S(stream));
+  const float hp[6] = {lr, l1, l2, l21, l2_shrinkage, lr_power};
+  return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, hp,
+                                    nullptr, today, S(stream));
 }
 int kv_apply_adam(kv_table* var, kv_table* m_v, const int64_t* d_ids, const float* d_grad,
                   int64_t n, const int32_t* d_n, float lr, float beta1, float beta2, float epsilon,
                   float beta1_power, float beta2_power, uint16_t today, kv_stream stream) {
   MultiGuard g(var, m_v, nullptr);
   if (g.rc) return g.rc;
-  return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, lr, beta1, beta2, epsilon,
-                       beta1_power, beta2_power, today, S(stream));
+  const float hp[6] = {lr, beta1, beta2, epsilon, beta1_power, beta2_power};
+  return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, hp, nullptr, today, S(stream));
+}
+
+// Device-resident hyper-parameters (TF scalar inputs that were not pinned to HostMemory).
+int kv_apply_adagrad_dev(kv_table* var, kv_table* accum, const int64_t* d_ids,
+                         const float* d_grad, int64_t n, const int32_t* d_n, const float* d_hp,
+                         int update_slots, uint16_t today, kv_stream stream) {
+  MultiGuard g(var, accum, nullptr);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, nullptr, d_hp, update_slots,
+                          today, S(stream));
+}
+int kv_apply_group_adam_v4_dev(kv_table* var, kv_table* mvl, const int64_t* d_ids,
+                               const float* d_grad, int64_t n, const int32_t* d_n,
+                               const float* d_hp, uint16_t today, kv_stream stream) {
+  MultiGuard g(var, mvl, nullptr);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today,
+                                S(stream));
+}
+int kv_apply_sparse_group_ftrl_dev(kv_table* var, kv_table* accum, kv_table* linear,
+                                   const int64_t* d_ids, const float* d_grad, int64_t n,
+                                   const int32_t* d_n, const float* d_hp, uint16_t today,
+                                   kv_stream stream) {
+  MultiGuard g(var, accum, linear);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n,
+                                    nullptr, d_hp, today, S(stream));
+}
+int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids, const float* d_grad,
+                      int64_t n, const int32_t* d_n, const float* d_hp, uint16_t today,
+                      kv_stream stream) {
+  MultiGuard g(var, m_v, nullptr);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream));
 }
 
 int kv_workspace_create(kv_workspace** out) {

@@ -13,7 +13,6 @@ namespace kvhbm {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int UNR = 4;
 
 // modes of a lane's id after phase 1
 constexpr int M_SKIP = -1;   // no output (padding lane / filtered id)
@@ -30,6 +29,7 @@ template <int VEC, int CPL, bool INSERT>
 __global__ void __launch_bounds__(256)
 gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
               long long n, float* __restrict__ out, uint32_t today, int tpr) {
+  constexpr int UNR = CPL <= 2 ? 4 : (CPL == 4 ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const long long wpb = blockDim.x >> 5;
   const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -452,11 +452,13 @@ int launch_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
     if (g.vec == 4) {                                               \
       if (g.cpl == 1) return CALL(4, 1);                            \
       if (g.cpl == 2) return CALL(4, 2);                            \
-      return CALL(4, 4);                                            \
+      if (g.cpl <= 4) return CALL(4, 4);                            \
+      return CALL(4, 8);                                            \
     }                                                               \
     if (g.cpl == 1) return CALL(1, 1);                              \
     if (g.cpl == 2) return CALL(1, 2);                              \
-    return CALL(1, 4);                                              \
+    if (g.cpl <= 4) return CALL(1, 4);                              \
+    return CALL(1, 8);                                              \
   } while (0)
 
 int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
@@ -464,8 +466,6 @@ int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts,
   if (n <= 0) return 0;
   if (insert) KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
-  const int cpl = g.cpl == 3 ? 4 : g.cpl;
-  g.cpl = cpl;
 #define CALL(V, C) launch_gather<V, C>(tb, insert, ids, counts, n, out, today, st, g.tpr)
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL
@@ -476,7 +476,6 @@ int do_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t 
   if (n <= 0) return 0;
   KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
-  g.cpl = g.cpl == 3 ? 4 : g.cpl;
 #define CALL(V, C) launch_scatter<V, C>(tb, op, ids, upd, n, st, g.tpr)
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL
@@ -487,7 +486,6 @@ int do_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
   if (n <= 0) return 0;
   KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
-  g.cpl = g.cpl == 3 ? 4 : g.cpl;
 #define CALL(V, C) launch_insert<V, C>(tb, ids, values, n, filter_out, blacklist, st, g.tpr)
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL

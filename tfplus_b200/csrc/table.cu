@@ -243,9 +243,9 @@ Table::~Table() {
 int Table::create(int dim_, int thr, int64_t capacity_hint) {
   if (dim_ <= 0) return fail(1, "KvVariable: embedding dim must be positive");
   RowGeom g = row_geom(dim_);
-  if (g.cpl > 4)
+  if (g.cpl > 8)
     return fail(3, "KvVariable: embedding dim " + std::to_string(dim_) +
-                       " not supported (max 512 when a multiple of 4, else 128)");
+                       " not supported (max 1024 when a multiple of 4, else 256)");
   KV_CUDA(cudaGetDevice(&device));
   dim = dim_;
   row_stride = (dim + 3) / 4 * 4;
@@ -319,10 +319,25 @@ int Table::rehash(uint64_t new_capacity, cudaStream_t stream) {
   return 0;
 }
 
-int Table::ensure(int64_t n, cudaStream_t stream) {
+// Sizing policy.  Eager calls keep host-side upper bounds of the claimed slots and rows
+// (each call can insert at most n keys) and only read the device counters back - one stream
+// synchronisation - when a bound reaches a limit.  Under CUDA-graph capture nothing may
+// synchronise or allocate: the call only checks that the table already has room (kv_reserve
+// makes it) and books nothing, because the captured work runs later, any number of times;
+// after a capture the bounds are no longer bounds, so eager calls re-read the counters.
+int Table::ensure(int64_t n, cudaStream_t stream, bool exact) {
   if (n < 0) n = 0;
   const uint64_t un = (uint64_t)n;
-  if (used_ub + un > capacity / 2 || rows_ub + un > rows_mapped) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
+  if (cap != cudaStreamCaptureStatusNone) {
+    captured = true;
+    if (used_ub + un > capacity / 2 || rows_ub + un > rows_mapped)
+      return fail(2, "KvVariable would have to grow during CUDA-graph capture: call kv_reserve "
+                     "with the number of keys the captured work may insert first");
+    return 0;
+  }
+  if (exact || captured || used_ub + un > capacity / 2 || rows_ub + un > rows_mapped) {
     KV_TRY(sync_counters(stream));
     used_ub = h_ctr->used;
     rows_ub = h_ctr->rows_bump;

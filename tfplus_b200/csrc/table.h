@@ -81,6 +81,7 @@ struct Table {
   // host-side upper bounds, so that the steady state never synchronises
   uint64_t used_ub = 0;
   uint64_t rows_ub = 0;
+  bool captured = false;  // some call on this table was recorded into a CUDA graph
 
   std::mutex mu;
 
@@ -88,7 +89,7 @@ struct Table {
   int create(int dim, int enter_threshold, int64_t capacity_hint);
   TableView view() const;
   // Guarantee room for `n` more keys (slots at load <= 0.5 and rows).
-  int ensure(int64_t n, cudaStream_t stream);
+  int ensure(int64_t n, cudaStream_t stream, bool exact = false);
   // Copy the counters to the host (synchronises `stream`).
   int sync_counters(cudaStream_t stream);
   int rehash(uint64_t new_capacity, cudaStream_t stream);

@@ -504,6 +504,52 @@ def kv_variable_sparse_apply_adam(var, m_v, grad, indices, lr, beta1, beta2, eps
                                var.stream))
 
 
+def _hp(var, hparams, n):
+  if hparams.dtype != torch.float32 or hparams.numel() < n or hparams.device != var.device:
+    raise ValueError("InvalidArgument: hparams must be %d float32 scalars on %s" % (n, var.device))
+  return hparams.contiguous()
+
+
+def kv_variable_sparse_apply_adagrad_dev(var, accum, hparams, grad, indices, update_slots=True,
+                                         num_indices=None):
+  """KvVariableSparseApplyAdagrad with hparams = [lr] in device memory."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  hp = _hp(var, hparams, 1)
+  check(var._lib.kv_apply_adagrad_dev(var._live(), accum._live(), ids.data_ptr(), g.data_ptr(),
+                                      ids.numel(), _ptr(dn), hp.data_ptr(), int(update_slots),
+                                      today(), var.stream))
+
+
+def kv_variable_group_sparse_apply_adam_v4_dev(var, m_v_linear, grad, indices, hparams,
+                                               num_indices=None):
+  """KvVariableGroupSparseApplyAdamV4 with hparams = [lr, beta1_power, beta2_power, beta1,
+  beta2, epsilon, l1, l2, l21] in device memory (graph-capturable)."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  hp = _hp(var, hparams, 9)
+  check(var._lib.kv_apply_group_adam_v4_dev(var._live(), m_v_linear._live(), ids.data_ptr(),
+                                            g.data_ptr(), ids.numel(), _ptr(dn), hp.data_ptr(),
+                                            today(), var.stream))
+
+
+def kv_variable_sparse_group_sparse_apply_ftrl_v2_dev(var, accum, linear, grad, indices, hparams,
+                                                      num_indices=None):
+  """KvVariableSparseGroupSparseApplyFtrlV2 with hparams = [lr, l1, l2, l21, l2_shrinkage,
+  lr_power] in device memory."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  hp = _hp(var, hparams, 6)
+  check(var._lib.kv_apply_sparse_group_ftrl_dev(var._live(), accum._live(), linear._live(),
+                                                ids.data_ptr(), g.data_ptr(), ids.numel(),
+                                                _ptr(dn), hp.data_ptr(), today(), var.stream))
+
+
+def kv_variable_sparse_apply_adam_dev(var, m_v, grad, indices, hparams, num_indices=None):
+  """Fused tfplus-Adam with hparams = [lr, beta1, beta2, epsilon, beta1_power, beta2_power]."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  hp = _hp(var, hparams, 6)
+  check(var._lib.kv_apply_adam_dev(var._live(), m_v._live(), ids.data_ptr(), g.data_ptr(),
+                                   ids.numel(), _ptr(dn), hp.data_ptr(), today(), var.stream))
+
+
 # ---------------------------------------------------------------------------
 # stock TF ops on the path
 # ---------------------------------------------------------------------------
@@ -518,7 +564,7 @@ def unique(x, with_counts=False, sync=True):
   uniq = torch.empty(n, dtype=torch.int64, device=dev)
   idx = torch.empty(n, dtype=torch.int32, device=dev)
   counts = torch.empty(n, dtype=torch.int32, device=dev) if with_counts else None
-  num = torch.zeros(1, dtype=torch.int32, device=dev)
+  num = torch.empty(1, dtype=torch.int32, device=dev)
   ws = Workspace.get(dev)
   with torch.cuda.device(dev):
     check(_lib.load().kv_unique(ws.ptr, ids.data_ptr(), n, uniq.data_ptr(), idx.data_ptr(),
