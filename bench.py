@@ -372,6 +372,8 @@ class LocalStepper:
                            device=dev)
     self.betas = torch.tensor([HP["beta1"], HP["beta2"]], dtype=torch.float32, device=dev)
     self.graphs = {}
+    self.overlap = os.environ.get("KVHBM_BENCH_OVERLAP", "1") != "0"
+    self.side = torch.cuda.Stream(device=dev)
 
   def populate(self):
     torch, ops = self.torch, self.ops
@@ -407,8 +409,21 @@ class LocalStepper:
       self.hp[1:3].mul_(self.betas)   # beta1_power *= beta1, beta2_power *= beta2
 
   def step_eager(self, ids, grad, buf):
-    for name in self.STAGES:
-      self.stage(name, ids, grad, buf)
+    """gather and (unique -> segment_sum) only depend on the ids / gradients, so they run on
+    two streams and join before the apply (the fork/join is captured into the step graph)."""
+    torch = self.torch
+    if not self.overlap:
+      for name in self.STAGES:
+        self.stage(name, ids, grad, buf)
+      return buf["rows"]
+    main = torch.cuda.current_stream(self.dev)
+    self.side.wait_stream(main)
+    with torch.cuda.stream(self.side):
+      self.stage("unique", ids, grad, buf)
+      self.stage("segment_sum", ids, grad, buf)
+    self.stage("gather", ids, grad, buf)
+    main.wait_stream(self.side)
+    self.stage("apply", ids, grad, buf)
     return buf["rows"]
 
   def _capture(self, fn):

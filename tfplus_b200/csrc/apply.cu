@@ -104,15 +104,24 @@ __device__ __forceinline__ float clip_l1(float lin, float l1) {
   return a < -l1 ? -l1 : a;
 }
 
-// Per-lane probe of one slot-variable table: FindOrInsertUnsafe(key, ctx, nullptr),
-// kv_variable.h:382-416 (found: freq += 1, day = today; absent: ctor freq 1).
+// One slot-variable table of one key, resolved by the tile leader:
+// FindOrInsertUnsafe(key, ctx, nullptr), kv_variable.h:382-416 (found: freq += 1, day = today;
+// absent: EmbeddingValue ctor freq 1).  `r`/`pos`/`s` come from the read-only probe.  The
+// frequency atomic is issued here; *f_old is consumed by finish_frequency after the row math.
 template <int KIND>
-__device__ __forceinline__ int probe_slot_table(const TableView& t, long long key, uint32_t today,
-                                                long long* pos, uint32_t* ctl) {
-  Slot s;
-  bool claimed;
-  *pos = find_or_claim(t, key, &s, &claimed);
-  if (*pos < 0) return V_SKIP;
+__device__ __forceinline__ int resolve_slot_table(const TableView& t, long long key, int r,
+                                                  long long* pos, Slot s, uint32_t today,
+                                                  uint32_t* ctl, bool* f_lead, uint32_t* f_old) {
+  bool claimed = false;
+  if (r != 1) {
+    const int c = claim_slot(t, key, *pos);
+    if (c == 1) claimed = true;
+    else if (c == 0) *pos = find_or_claim(t, key, &s, &claimed);  // rare: lost the slot to another key
+    if (*pos < 0) return V_SKIP;
+    if (!claimed && c != 1) {  // a duplicate id of this launch inserted it meanwhile
+      s.ctl = ld_acquire_u32(&t.slots[*pos].ctl);
+    }
+  }
   if (claimed) {
     *ctl = alloc_row(t);
     // Adam reaches its slot through GatherOrInsert: insert_func writes {1, today}
@@ -120,11 +129,16 @@ __device__ __forceinline__ int probe_slot_table(const TableView& t, long long ke
     return V_CLAIM;
   }
   *ctl = s.ctl;
-  add_frequency(&t.slots[*pos].freq, 1u, today);
+  *f_old = atomicAdd(&t.slots[*pos].freq, 1u << 16);
+  *f_lead = true;
   return V_COPY;
 }
 
-template <int VEC, int CPL, int UNR, int KIND>
+// A tile of `tpr` lanes owns one id: its leader probes the value table and the slot table(s)
+// at the same time (independent loads in flight together), the tile then reads gradient +
+// value + slots once with 128-bit accesses, updates them in registers and writes them back.
+// 32 / tpr ids per warp keep enough warps resident to hide the IEEE sqrt / divide chains.
+template <int VEC, int CPL, int KIND>
 __global__ void __launch_bounds__(128)
 apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restrict__ ids,
              const float* __restrict__ grad, long long n, const int* __restrict__ d_n,
@@ -134,241 +148,240 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
   constexpr bool TWO = Kind<KIND>::TWO;
   const int lane = threadIdx.x & 31;
   const long long wpb = blockDim.x >> 5;
-  const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
-  const long long nwarps = gridDim.x * wpb;
-  const int kpi = 32 / tpr;
+  const int kpi = 32 / tpr;  // ids per warp
   const int tl = lane & (tpr - 1);
   const int tq = lane / tpr;
+  const int leader = tq * tpr;
   const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
   const int dim = var.dim;
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
 
-  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
-    const long long i = base + lane;
+  for (long long grp = blockIdx.x * wpb + (threadIdx.x >> 5); grp * kpi < n;
+       grp += (long long)gridDim.x * wpb) {
+    const long long i = grp * kpi + tq;
     const bool valid = i < n;
-    const long long key = valid ? ids[i] : 0;
 
-    // ---------------- phase 1: one lane per id ----------------
+    // ---------------- phase 1: the tile leader resolves the id in every table ----------------
+    long long key = 0;
     int vmode = V_SKIP, amode = V_SKIP, bmode = V_SKIP;
     long long vpos = -1, apos = -1, bpos = -1;
     uint32_t vctl = 0, actl = 0, bctl = 0;
-    if (valid) {
-      Slot s;
-      bool claimed;
-      vpos = find_or_claim(var, key, &s, &claimed);
+    bool a_lead = false, b_lead = false;
+    uint32_t a_old = 0, b_old = 0;
+    if (valid && tl == 0) {
+      key = ids[i];
+      Probe pv = probe_begin(var, key), pa = probe_begin(sa, key), pb = probe_begin(sb, key);
+      int rv = -1, ra = -1, rb = TWO ? -1 : 0;
+      Slot sv, ssa, ssb, x0, x1, y0, y1, z0, z1;
+      for (unsigned long long guard = 0; guard <= var.mask + sa.mask + sb.mask; ++guard) {
+        if (rv < 0) { x0 = load_slot(var.slots + pv.bucket * 2); x1 = load_slot(var.slots + pv.bucket * 2 + 1); }
+        if (ra < 0) { y0 = load_slot(sa.slots + pa.bucket * 2); y1 = load_slot(sa.slots + pa.bucket * 2 + 1); }
+        if (TWO && rb < 0) { z0 = load_slot(sb.slots + pb.bucket * 2); z1 = load_slot(sb.slots + pb.bucket * 2 + 1); }
+        if (rv < 0) rv = probe_step(var, key, &pv, x0, x1, &vpos, &sv);
+        if (ra < 0) ra = probe_step(sa, key, &pa, y0, y1, &apos, &ssa);
+        if (TWO && rb < 0) rb = probe_step(sb, key, &pb, z0, z1, &bpos, &ssb);
+        if (rv >= 0 && ra >= 0 && rb >= 0) break;
+      }
+      // value table: FindOrInsertUnsafe(key, ctx, &should_filter), kv_variable.h:382-408
+      bool claimed = false;
+      if (rv != 1) {
+        const int c = claim_slot(var, key, vpos);
+        if (c == 1) claimed = true;
+        else if (c == 0) vpos = find_or_claim(var, key, &sv, &claimed);
+        if (!claimed && vpos >= 0) {  // inserted meanwhile by a duplicate id of this launch
+          sv.ctl = ld_acquire_u32(&var.slots[vpos].ctl);
+          sv.freq = 1u << 16;
+        }
+      }
       if (vpos >= 0) {
         if (claimed) {
           vctl = alloc_row(var);
           var.slots[vpos].freq = 1u << 16;
           vmode = V_CLAIM;
         } else {
-          vctl = s.ctl;
-          if (KIND != K_ADAM && freq_count(s.freq) < var.enter_threshold) vmode = V_SKIP;
+          vctl = sv.ctl;
+          if (KIND != K_ADAM && freq_count(sv.freq) < var.enter_threshold) vmode = V_SKIP;
           else if (vctl & CTL_BLACK) vmode = KIND == K_ADAM ? V_KEEP : V_ZERO;
           else vmode = V_COPY;
         }
       }
       if (vmode != V_SKIP) {
-        amode = probe_slot_table<KIND>(sa, key, today, &apos, &actl);
-        if (TWO) bmode = probe_slot_table<KIND>(sb, key, today, &bpos, &bctl);
+        amode = resolve_slot_table<KIND>(sa, key, ra, &apos, ssa, today, &actl, &a_lead, &a_old);
+        if (TWO)
+          bmode = resolve_slot_table<KIND>(sb, key, rb, &bpos, ssb, today, &bctl, &b_lead, &b_old);
+        if (amode == V_SKIP || (TWO && bmode == V_SKIP)) vmode = V_SKIP;
       }
     }
-    float* vrow = vmode != V_SKIP ? row_ptr(var, vctl) : nullptr;
-    float* arow = amode != V_SKIP ? row_ptr(sa, actl) : nullptr;
-    float* brow = (TWO && bmode != V_SKIP) ? row_ptr(sb, bctl) : nullptr;
+    // hand the verdicts to the tile
+    const int vm = __shfl_sync(FULL, vmode, leader);
+    const int am = __shfl_sync(FULL, amode, leader);
+    const int bm = TWO ? __shfl_sync(FULL, bmode, leader) : V_SKIP;
+    const uint32_t vc = __shfl_sync(FULL, vctl, leader);
+    const uint32_t ac = __shfl_sync(FULL, actl, leader);
+    const uint32_t bc = TWO ? __shfl_sync(FULL, bctl, leader) : 0u;
+    const bool on = vm != V_SKIP;
+    float* vp = row_ptr(var, vc);
+    float* ap = row_ptr(sa, ac);
+    float* bp = row_ptr(sb, bc);
 
-    // verdicts collected by each id's owner lane
-    bool v_under = (vctl & CTL_UNDER) != 0, a_under = (actl & CTL_UNDER) != 0,
-         b_under = (bctl & CTL_UNDER) != 0;
-    bool v_black = false;
-
-    // ---------------- phase 2: tiles move and update rows ----------------
-    for (int it = 0; it < tpr; it += UNR) {
-      Chunk<VEC> g[UNR][CPL], w[UNR][CPL], s[UNR][PARTS][CPL];
-      int vm[UNR], am[UNR], bm[UNR];
-      float *vp[UNR], *ap[UNR], *bp[UNR];
+    // ---------------- phase 2: the tile moves and updates the rows ----------------
+    Chunk<VEC> g[CPL], w[CPL], s[PARTS][CPL];
+    {
+      long long v1 = -1, v2 = -1, a1 = -1, a2 = -1, b1 = -1, b2 = -1;
+      if (__any_sync(FULL, vm == V_CLAIM || am == V_CLAIM || bm == V_CLAIM)) {
+        const long long k = shfl_ll(key, leader);
+        if (vm == V_CLAIM) init_rows_of(var, k, &v1, &v2);
+        if (am == V_CLAIM) init_rows_of(sa, k, &a1, &a2);
+        if (TWO && bm == V_CLAIM) init_rows_of(sb, k, &b1, &b2);
+      }
+      const float* gp = grad + i * (long long)dim;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        vm[u] = V_SKIP; am[u] = V_SKIP; bm[u] = V_SKIP;
-        vp[u] = ap[u] = bp[u] = nullptr;
-        if (it + u < tpr) {
-          const int kl = (it + u) * kpi + tq;
-          vm[u] = __shfl_sync(FULL, vmode, kl);
-          am[u] = __shfl_sync(FULL, amode, kl);
-          vp[u] = shfl_ptr(vrow, kl);
-          ap[u] = shfl_ptr(arow, kl);
-          if (TWO) { bm[u] = __shfl_sync(FULL, bmode, kl); bp[u] = shfl_ptr(brow, kl); }
-          const long long k = shfl_ll(key, kl);
-          const bool on = vm[u] != V_SKIP;
-          long long v1 = -1, v2 = -1, a1 = -1, a2 = -1, b1 = -1, b2 = -1;
-          if (vm[u] == V_CLAIM) init_rows_of(var, k, &v1, &v2);
-          if (am[u] == V_CLAIM) init_rows_of(sa, k, &a1, &a2);
-          if (TWO && bm[u] == V_CLAIM) init_rows_of(sb, k, &b1, &b2);
-          const float* gp = grad + (base + kl) * (long long)dim;
+      for (int q = 0; q < CPL; ++q) {
+        const int off = (q * tpr + tl) * VEC;
+        const bool in = on && off < dim;
+        if (in) g[q].load_stream(gp + off); else chunk_zero(g[q]);
+        if (in && (vm == V_COPY || vm == V_KEEP)) w[q].load_cg(vp + off);
+        else if (in && vm == V_CLAIM) init_chunk<VEC>(var, v1, v2, off, w[q]);
+        else chunk_zero(w[q]);
 #pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            const int off = (q * tpr + tl) * VEC;
-            const bool in = on && off < dim;
-            if (in) g[u][q].load_stream(gp + off); else chunk_zero(g[u][q]);
-            if (in && (vm[u] == V_COPY || vm[u] == V_KEEP)) w[u][q].load_cg(vp[u] + off);
-            else if (in && vm[u] == V_CLAIM) init_chunk<VEC>(var, v1, v2, off, w[u][q]);
-            else chunk_zero(w[u][q]);
-#pragma unroll
-            for (int r = 0; r < PARTS; ++r) {
-              const bool second = TWO && r == 1;
-              const int md = second ? bm[u] : am[u];
-              float* rp = second ? bp[u] : ap[u];
-              const int soff = (TWO ? 0 : r * dim) + off;
-              if (in && md == V_COPY) s[u][r][q].load_cg(rp + soff);
-              else if (in && md == V_CLAIM) {
-                if (second) init_chunk<VEC>(sb, b1, b2, soff, s[u][r][q]);
-                else init_chunk<VEC>(sa, a1, a2, soff, s[u][r][q]);
-              } else chunk_zero(s[u][r][q]);
-            }
-          }
+        for (int r = 0; r < PARTS; ++r) {
+          const bool second = TWO && r == 1;
+          const int md = second ? bm : am;
+          float* rp = second ? bp : ap;
+          const int soff = (TWO ? 0 : r * dim) + off;
+          if (in && md == V_COPY) s[r][q].load_cg(rp + soff);
+          else if (in && md == V_CLAIM) {
+            if (second) init_chunk<VEC>(sb, b1, b2, soff, s[r][q]);
+            else init_chunk<VEC>(sa, a1, a2, soff, s[r][q]);
+          } else chunk_zero(s[r][q]);
         }
       }
+    }
 
+    bool vbig = false, abig = false, bbig = false, black = false;
+    if (KIND == K_ADAGRAD) {
+      // training_ops.cc:1473-1482.  Under-threshold flags are those of the insert
+      // (kv_variable.h:398), Adagrad never refreshes them.
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (it + u >= tpr) continue;  // uniform across the warp
-        const bool on = vm[u] != V_SKIP;
-        bool vbig = false, abig = false, bbig = false, black = false;
-
-        if (KIND == K_ADAGRAD) {
-          // training_ops.cc:1473-1482.  Under-threshold flags are those of the
-          // insert (kv_variable.h:398), Adagrad never refreshes them.
+      for (int q = 0; q < CPL; ++q) {
+        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+        abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
 #pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
-            abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF);
+        for (int e = 0; e < VEC; ++e) {
+          const float gg = g[q].v[e];
+          float a = s[0][q].v[e];
+          if (p.update_slots) a += gg * gg;
+          s[0][q].v[e] = a;
+          if (dim > 1) w[q].v[e] -= (p.lr * gg) * (1.0f / sqrtf(a));
+          else w[q].v[e] -= (p.lr * gg) / sqrtf(a);
+        }
+      }
+    } else if (KIND == K_ADAM) {
+      // python/training/adam.py:116-156, every TF op rounded on its own
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              const float gg = g[u][q].v[e];
-              float a = s[u][0][q].v[e];
-              if (p.update_slots) a += gg * gg;
-              s[u][0][q].v[e] = a;
-              if (dim > 1) w[u][q].v[e] -= (p.lr * gg) * (1.0f / sqrtf(a));
-              else w[u][q].v[e] -= (p.lr * gg) / sqrtf(a);
-            }
+      for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float gg = g[q].v[e];
+          const float m_t = (s[0][q].v[e] * p.beta1) + (gg * p.one_minus_beta1);
+          const float v_t = (s[1][q].v[e] * p.beta2) + ((gg * gg) * p.one_minus_beta2);
+          s[0][q].v[e] = m_t;
+          s[1][q].v[e] = v_t;
+          if (vm != V_KEEP) w[q].v[e] -= (p.alpha * m_t) / (sqrtf(v_t) + p.epsilon);
+        }
+        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+        abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
+                chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
+      }
+    } else {
+      // GroupAdam v4 (training_ops.cc:7166-7195) / SparseGroupFtrl (:713-751)
+      Chunk<VEC> z[CPL], den[CPL], gs[CPL];
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float gg = g[q].v[e];
+          const float wv = w[q].v[e];
+          float lin;
+          if (KIND == K_GROUP_ADAM) {
+            const float m = p.beta1 * s[0][q].v[e] + p.one_minus_beta1 * gg;
+            const float vo = s[1][q].v[e];
+            const float nv = p.beta2 * vo + p.one_minus_beta2 * (gg * gg);
+            const float sq = sqrtf(nv);
+            lin = s[2][q].v[e];
+            if (p.later_step) lin += p.alpha * m - (sq - sqrtf(vo)) * wv;
+            else lin += p.alpha * m - (sq + p.epsilon) * wv;
+            s[0][q].v[e] = m;
+            s[1][q].v[e] = nv;
+            s[2][q].v[e] = lin;
+            den[q].v[e] = sq + p.epsilon + p.l2x2;
+            gs[q].v[e] = 0.f;
+          } else {
+            const float a = s[0][q].v[e];
+            const float gsh = gg + p.shrink2 * wv;
+            const float na = a + gsh * gsh;
+            const float pna = powp(p, na);
+            lin = s[1][q].v[e];
+            lin += gsh - (pna - powp(p, a)) / p.lr * wv;
+            s[1][q].v[e] = lin;
+            gs[q].v[e] = gsh;
+            den[q].v[e] = pna / p.lr + p.l2x2;
           }
-        } else if (KIND == K_ADAM) {
-          // python/training/adam.py:116-156, every TF op rounded on its own
+          const float zz = clip_l1(lin, p.l1) - lin;
+          z[q].v[e] = zz;
+          ss += zz * zz;
+        }
+      }
+      for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+      const float nrm = sqrtf(ss);
+      black = !(nrm > p.l21_norm);
+      const float c = 1.0f - p.l21_norm / nrm;
 #pragma unroll
-          for (int q = 0; q < CPL; ++q) {
+      for (int q = 0; q < CPL; ++q) {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              const float gg = g[u][q].v[e];
-              const float m_t = (s[u][0][q].v[e] * p.beta1) + (gg * p.one_minus_beta1);
-              const float v_t = (s[u][1][q].v[e] * p.beta2) + ((gg * gg) * p.one_minus_beta2);
-              s[u][0][q].v[e] = m_t;
-              s[u][1][q].v[e] = v_t;
-              if (vm[u] != V_KEEP) w[u][q].v[e] -= (p.alpha * m_t) / (sqrtf(v_t) + p.epsilon);
-            }
-            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
-            abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF) |
-                    chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF);
+        for (int e = 0; e < VEC; ++e) {
+          if (!black) w[q].v[e] = z[q].v[e] * c / den[q].v[e];
+          if (KIND == K_FTRL) {
+            // accum += grad_to_use.square(), re-evaluated with the new var (old var after
+            // a blacklist); see oracle/kv_oracle.cc
+            const float g2 = black ? gs[q].v[e] : g[q].v[e] + p.shrink2 * w[q].v[e];
+            s[0][q].v[e] += g2 * g2;
           }
+        }
+        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+        if (KIND == K_GROUP_ADAM) {
+          abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
+                  chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF) |
+                  chunk_over_cutoff(s[2][q], DEFAULT_CUTOFF);
         } else {
-          // GroupAdam v4 (training_ops.cc:7166-7195) / SparseGroupFtrl (:713-751)
-          Chunk<VEC> z[CPL], den[CPL], gs[CPL];
-          float ss = 0.f;
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              const float gg = g[u][q].v[e];
-              const float wv = w[u][q].v[e];
-              float lin;
-              if (KIND == K_GROUP_ADAM) {
-                const float m = p.beta1 * s[u][0][q].v[e] + p.one_minus_beta1 * gg;
-                const float vo = s[u][1][q].v[e];
-                const float nv = p.beta2 * vo + p.one_minus_beta2 * (gg * gg);
-                const float sq = sqrtf(nv);
-                lin = s[u][2][q].v[e];
-                if (p.later_step) lin += p.alpha * m - (sq - sqrtf(vo)) * wv;
-                else lin += p.alpha * m - (sq + p.epsilon) * wv;
-                s[u][0][q].v[e] = m;
-                s[u][1][q].v[e] = nv;
-                s[u][2][q].v[e] = lin;
-                den[q].v[e] = sq + p.epsilon + p.l2x2;
-              } else {
-                const float a = s[u][0][q].v[e];
-                const float gsh = gg + p.shrink2 * wv;
-                const float na = a + gsh * gsh;
-                const float pna = powp(p, na);
-                lin = s[u][1][q].v[e];
-                lin += gsh - (pna - powp(p, a)) / p.lr * wv;
-                s[u][1][q].v[e] = lin;
-                gs[q].v[e] = gsh;
-                den[q].v[e] = pna / p.lr + p.l2x2;
-              }
-              const float zz = clip_l1(lin, p.l1) - lin;
-              z[q].v[e] = zz;
-              ss += zz * zz;
-            }
-          }
-          for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
-          const float nrm = sqrtf(ss);
-          black = !(nrm > p.l21_norm);
-          const float c = 1.0f - p.l21_norm / nrm;
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              const float w_old = w[u][q].v[e];
-              if (!black) w[u][q].v[e] = z[q].v[e] * c / den[q].v[e];
-              if (KIND == K_FTRL) {
-                // accum += grad_to_use.square(), re-evaluated with the new var
-                // (old var after a blacklist); see oracle/kv_oracle.cc
-                const float g2 = black ? gs[q].v[e] : g[u][q].v[e] + p.shrink2 * w[u][q].v[e];
-                s[u][0][q].v[e] += g2 * g2;
-                (void)w_old;
-              }
-            }
-            vbig |= chunk_over_cutoff(w[u][q], DEFAULT_CUTOFF);
-            if (KIND == K_GROUP_ADAM) {
-              abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF) |
-                      chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF) |
-                      chunk_over_cutoff(s[u][2][q], DEFAULT_CUTOFF);
-            } else {
-              abig |= chunk_over_cutoff(s[u][0][q], DEFAULT_CUTOFF);
-              bbig |= chunk_over_cutoff(s[u][1][q], DEFAULT_CUTOFF);
-            }
-          }
-        }
-
-        // write back
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-          const int off = (q * tpr + tl) * VEC;
-          if (on && off < dim) {
-            if (vm[u] != V_KEEP) w[u][q].store(vp[u] + off);
-#pragma unroll
-            for (int r = 0; r < PARTS; ++r) {
-              const bool second = TWO && r == 1;
-              float* rp = second ? bp[u] : ap[u];
-              s[u][r][q].store(rp + (TWO ? 0 : r * dim) + off);
-            }
-          }
-        }
-        const unsigned vb = __ballot_sync(FULL, vbig);
-        const unsigned ab = __ballot_sync(FULL, abig);
-        const unsigned bb = TWO ? __ballot_sync(FULL, bbig) : 0u;
-        const unsigned kb = __ballot_sync(FULL, black);
-        if (lane / kpi == it + u) {
-          const int sh = (lane % kpi) * tpr;
-          v_under = ((vb >> sh) & tmask) == 0;
-          a_under = ((ab >> sh) & tmask) == 0;
-          b_under = ((bb >> sh) & tmask) == 0;
-          v_black = ((kb >> sh) & 1u) != 0;
+          abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
+          bbig |= chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
         }
       }
     }
 
-    // ---------------- phase 3: publish flags ----------------
-    if (vmode != V_SKIP) {
-      // value row
+    // write back
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int off = (q * tpr + tl) * VEC;
+      if (on && off < dim) {
+        if (vm != V_KEEP) w[q].store(vp + off);
+#pragma unroll
+        for (int r = 0; r < PARTS; ++r) {
+          const bool second = TWO && r == 1;
+          float* rp = second ? bp : ap;
+          s[r][q].store(rp + (TWO ? 0 : r * dim) + off);
+        }
+      }
+    }
+    const int sh = tq * tpr;
+    const bool v_under = ((__ballot_sync(FULL, vbig) >> sh) & tmask) == 0;
+    const bool a_under = ((__ballot_sync(FULL, abig) >> sh) & tmask) == 0;
+    const bool b_under = TWO ? ((__ballot_sync(FULL, bbig) >> sh) & tmask) == 0 : false;
+
+    // ---------------- phase 3: the leader publishes flags ----------------
+    if (tl == 0 && vmode != V_SKIP) {
       uint32_t nv = CTL_READY | (vctl & CTL_ROW_MASK);
       if (KIND == K_ADAGRAD) {
         if (vmode == V_CLAIM) nv |= v_under ? CTL_UNDER : 0u;       // insert-time flag
@@ -378,22 +391,22 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
         if (vmode == V_KEEP) nv = vctl;
         else nv |= v_under ? CTL_UNDER : 0u;                         // ScatterUpdate refresh
       } else {
-        if (v_black) nv |= CTL_BLACK | CTL_UNDER;                    // MarkBlacklistUnsafe
+        if (black) nv |= CTL_BLACK | CTL_UNDER;                      // MarkBlacklistUnsafe
         else nv |= v_under ? CTL_UNDER : 0u;                         // CoverUpdateUnsafe
       }
-      if (vmode == V_CLAIM) __threadfence();
+      if (vmode == V_CLAIM || amode == V_CLAIM || bmode == V_CLAIM) __threadfence();
       if (nv != vctl || vmode == V_CLAIM) var.slots[vpos].ctl = nv;
 
       uint32_t na = CTL_READY | (actl & CTL_ROW_MASK);
       if (KIND == K_ADAGRAD) na |= amode == V_CLAIM ? (a_under ? CTL_UNDER : 0u) : (actl & CTL_UNDER);
       else na |= a_under ? CTL_UNDER : 0u;
-      if (amode == V_CLAIM) __threadfence();
       if (na != actl || amode == V_CLAIM) sa.slots[apos].ctl = na;
+      if (a_lead) finish_frequency(&sa.slots[apos].freq, a_old, 1u, today);
 
       if (TWO) {
-        uint32_t nb = CTL_READY | (bctl & CTL_ROW_MASK) | (b_under ? CTL_UNDER : 0u);
-        if (bmode == V_CLAIM) __threadfence();
+        const uint32_t nb = CTL_READY | (bctl & CTL_ROW_MASK) | (b_under ? CTL_UNDER : 0u);
         if (nb != bctl || bmode == V_CLAIM) sb.slots[bpos].ctl = nb;
+        if (b_lead) finish_frequency(&sb.slots[bpos].freq, b_old, 1u, today);
       }
     }
   }
@@ -403,10 +416,11 @@ template <int VEC, int CPL, int KIND>
 int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
                  int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
                  uint16_t today, cudaStream_t st, int tpr) {
-  constexpr int UNR = CPL == 1 ? 4 : (CPL == 2 ? 2 : 1);
-  const int blocks = blocks_for(n, 128, var->device, 16);
+  const int kpi = 32 / tpr;
+  const int64_t warps = (n + kpi - 1) / kpi;
+  const int blocks = blocks_for(warps, 4, var->device, 16);
   TableView vb = sb ? sb->view() : sa->view();
-  apply_kernel<VEC, CPL, UNR, KIND><<<blocks, 128, 0, st>>>(
+  apply_kernel<VEC, CPL, KIND><<<blocks, 128, 0, st>>>(
       var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,
       d_hp, today, tpr);
   KV_LAUNCHED();

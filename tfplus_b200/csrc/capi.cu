@@ -19,6 +19,7 @@ int do_insert(Table*, const int64_t*, const float*, int64_t, const uint8_t*, con
               cudaStream_t);
 int do_get_count(Table*, const int64_t*, int64_t, int32_t*, cudaStream_t);
 int do_get_timestamp(Table*, const int64_t*, int64_t, uint32_t*, uint16_t, cudaStream_t);
+int set_trace(unsigned long long* d_buf);
 int do_permute_rows(bool scatter, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
 
 int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
@@ -379,6 +380,7 @@ int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n, const in
   return do_partition_ids(ws->w, d_ids, n, d_n, num_shards, mode, d_sorted_ids, d_perm,
                           d_shard_counts, S(stream));
 }
+int kv_debug_set_trace(void* d_buf) { return set_trace(static_cast<unsigned long long*>(d_buf)); }
 int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
                     kv_stream stream) {
   return do_permute_rows(false, d_src, d_perm, n, dim, d_out, S(stream));

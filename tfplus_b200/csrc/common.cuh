@@ -48,7 +48,7 @@ struct Counters {
 struct TableView {
   Slot* slots;
   unsigned long long mask;  // capacity - 1
-  int shift;                // 64 - log2(capacity)
+  int shift;                // 64 - log2(capacity / 2): hash -> home bucket
   float* rows;
   int dim;
   int row_stride;  // floats, multiple of 4
@@ -67,10 +67,6 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
   return x;
 }
 constexpr unsigned long long GOLDEN = 0x9e3779b97f4a7c15ULL;
-
-__device__ __forceinline__ unsigned long long home_slot(const TableView& t, long long key) {
-  return mix64((unsigned long long)key) >> t.shift;
-}
 
 // ---- memory access helpers -------------------------------------------------
 __device__ __forceinline__ Slot load_slot(const Slot* p) {
@@ -92,16 +88,71 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 }
 
 // ---- probing ------------------------------------------------------------------
+// Bucketised linear probing: a bucket is two adjacent slots = one 32-byte DRAM
+// sector, fetched with two 128-bit loads that the memory system merges.  A key
+// lives in the first free slot (in bucket order) at or after its home bucket,
+// so at load <= 0.5 almost every lookup is a single dependent memory round trip.
+__device__ __forceinline__ unsigned long long home_bucket(const TableView& t, long long key) {
+  return mix64((unsigned long long)key) >> t.shift;  // shift = 64 - log2(capacity / 2)
+}
+
+// A resumable probe: advances until it finds `key` or the first EMPTY slot on its path.
+struct Probe {
+  unsigned long long bucket;
+  int sub;  // next slot inside the bucket to examine
+};
+__device__ __forceinline__ Probe probe_begin(const TableView& t, long long key) {
+  Probe p;
+  p.bucket = home_bucket(t, key);
+  p.sub = 0;
+  return p;
+}
+// Examines one bucket (s0, s1 = its two slots).  Returns 1 found (*pos, *out set), 0 reached
+// an EMPTY slot (*pos = that slot), -1 keep going (p advanced to the next bucket).
+__device__ __forceinline__ int probe_step(const TableView& t, long long key, Probe* p,
+                                          const Slot& s0, const Slot& s1, long long* pos,
+                                          Slot* out) {
+  if (p->sub == 0) {
+    if (s0.key == key) { *pos = (long long)(p->bucket * 2); *out = s0; return 1; }
+    if (s0.key == KEY_EMPTY) { *pos = (long long)(p->bucket * 2); return 0; }
+  }
+  if (s1.key == key) { *pos = (long long)(p->bucket * 2 + 1); *out = s1; return 1; }
+  if (s1.key == KEY_EMPTY) { *pos = (long long)(p->bucket * 2 + 1); p->sub = 1; return 0; }
+  p->bucket = (p->bucket + 1) & (t.mask >> 1);
+  p->sub = 0;
+  return -1;
+}
+// After a failed claim of the EMPTY slot `pos` (another key took it): step past it.
+__device__ __forceinline__ void probe_skip(const TableView& t, Probe* p, long long pos) {
+  if (pos & 1) { p->bucket = (p->bucket + 1) & (t.mask >> 1); p->sub = 0; }
+  else p->sub = 1;
+}
+
 // Read-only lookup.  Returns the slot index or -1.
 __device__ __forceinline__ long long find_slot(const TableView& t, long long key, Slot* out) {
-  unsigned long long pos = home_slot(t, key);
-  for (unsigned long long probes = 0; probes <= t.mask; ++probes) {
-    Slot s = load_slot(t.slots + pos);
-    if (s.key == key) { *out = s; return (long long)pos; }
-    if (s.key == KEY_EMPTY) return -1;
-    pos = (pos + 1) & t.mask;
+  Probe p = probe_begin(t, key);
+  for (unsigned long long n = 0; n <= (t.mask >> 1); ++n) {
+    const Slot s0 = load_slot(t.slots + p.bucket * 2);
+    const Slot s1 = load_slot(t.slots + p.bucket * 2 + 1);
+    long long pos;
+    const int r = probe_step(t, key, &p, s0, s1, &pos, out);
+    if (r == 1) return pos;
+    if (r == 0) return -1;
   }
   return -1;
+}
+
+// Try to claim the empty slot `pos` for `key`.  1 = claimed, 2 = the same key got there first
+// (found, possibly not yet published), 0 = another key took it: keep probing.
+__device__ __forceinline__ int claim_slot(const TableView& t, long long key, long long pos) {
+  const unsigned long long old = atomicCAS(
+      reinterpret_cast<unsigned long long*>(&t.slots[pos].key), (unsigned long long)KEY_EMPTY,
+      (unsigned long long)key);
+  if (old == (unsigned long long)KEY_EMPTY) {
+    atomicAdd(&t.ctr->used, 1ULL);
+    return 1;
+  }
+  return old == (unsigned long long)key ? 2 : 0;
 }
 
 // Find-or-claim.  Returns the slot index; *claimed is true when this thread
@@ -110,27 +161,23 @@ __device__ __forceinline__ long long find_slot(const TableView& t, long long key
 // claimed=false and may see ctl without CTL_READY.
 __device__ __forceinline__ long long find_or_claim(const TableView& t, long long key,
                                                    Slot* out, bool* claimed) {
-  unsigned long long pos = home_slot(t, key);
+  Probe p = probe_begin(t, key);
   *claimed = false;
-  for (unsigned long long probes = 0; probes <= t.mask; ++probes) {
-    Slot s = load_slot(t.slots + pos);
-    if (s.key == key) { *out = s; return (long long)pos; }
-    if (s.key == KEY_EMPTY) {
-      unsigned long long old = atomicCAS(
-          reinterpret_cast<unsigned long long*>(&t.slots[pos].key),
-          (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-      if (old == (unsigned long long)KEY_EMPTY) {
-        atomicAdd(&t.ctr->used, 1ULL);
-        *claimed = true;
-        out->key = key; out->freq = 0; out->ctl = 0;
-        return (long long)pos;
+  for (unsigned long long n = 0; n <= t.mask + 2; ++n) {
+    const Slot s0 = load_slot(t.slots + p.bucket * 2);
+    const Slot s1 = load_slot(t.slots + p.bucket * 2 + 1);
+    long long pos;
+    const int r = probe_step(t, key, &p, s0, s1, &pos, out);
+    if (r == 1) return pos;
+    if (r == 0) {
+      const int c = claim_slot(t, key, pos);
+      if (c) {
+        *claimed = c == 1;
+        out->key = key; out->freq = 0; out->ctl = 0;  // a loser re-reads ctl
+        return pos;
       }
-      if (old == (unsigned long long)key) {
-        out->key = key; out->freq = 0; out->ctl = 0;  // caller re-reads ctl
-        return (long long)pos;
-      }
+      probe_skip(t, &p, pos);
     }
-    pos = (pos + 1) & t.mask;
   }
   return -1;  // table full: the host sizing guarantees this cannot happen
 }
@@ -162,13 +209,17 @@ __device__ __forceinline__ float* row_ptr(const TableView& t, uint32_t ctl) {
 //    otherwise it is the exact sum: min(65535, sum) as utility.h:65-70;
 //  * the day changes once per key per day: only then AND it out and OR it in
 //    (all writers of one launch write the same `today`).
-__device__ __forceinline__ void add_frequency(uint32_t* freq, uint32_t cnt, uint32_t today) {
-  uint32_t old = atomicAdd(freq, cnt << 16);
+// Second half of add_frequency, given the value the atomicAdd returned.
+__device__ __forceinline__ void finish_frequency(uint32_t* freq, uint32_t old, uint32_t cnt,
+                                                 uint32_t today) {
   if ((old >> 16) + cnt > 0xFFFFu) atomicOr(freq, 0xFFFF0000u);
   if ((old & 0xFFFFu) != today) {
     atomicAnd(freq, 0xFFFF0000u);
     atomicOr(freq, today);
   }
+}
+__device__ __forceinline__ void add_frequency(uint32_t* freq, uint32_t cnt, uint32_t today) {
+  finish_frequency(freq, atomicAdd(freq, cnt << 16), cnt, today);
 }
 // SaturateMaxFrequency, utility.h:47-49 (including its wrap of negative counts).
 __device__ __forceinline__ uint32_t saturate_count(int c) {
@@ -210,6 +261,16 @@ template <> struct Chunk<4> {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  __device__ __forceinline__ void load_plain(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  // weak load that does not allocate in L1: rows are never L1-resident, so a row written by
+  // another SM earlier in the same launch can never be read stale
+  __device__ __forceinline__ void load_na(const float* p) {
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  }
   __device__ __forceinline__ void load_stream(const float* p) {
     float4 t = __ldcs(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -225,6 +286,10 @@ template <> struct Chunk<1> {
   float v[1];
   __device__ __forceinline__ void load_cg(const float* p) { v[0] = __ldcg(p); }
   __device__ __forceinline__ void load_nc(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void load_plain(const float* p) { v[0] = *p; }
+  __device__ __forceinline__ void load_na(const float* p) {
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
+  }
   __device__ __forceinline__ void load_stream(const float* p) { v[0] = __ldcs(p); }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
   __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, v[0]); }

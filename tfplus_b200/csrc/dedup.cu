@@ -10,6 +10,11 @@ struct Workspace {
   int device = 0;
   void* buf = nullptr;
   size_t bytes = 0;
+  // unique(): scratch tables + selector, see UScratch
+  void* ubuf = nullptr;
+  unsigned long long ucap = 0;
+  int unb = 0;
+  void* wiped_buf = nullptr;  // ubuf for which unique_wipe_kernel has been enqueued
   int grab(size_t need, cudaStream_t st) {
     if (need <= bytes) return 0;
     KV_CUDA(cudaStreamSynchronize(st));
@@ -21,7 +26,10 @@ struct Workspace {
     bytes = want;
     return 0;
   }
-  ~Workspace() { if (buf) cudaFree(buf); }
+  ~Workspace() {
+    if (buf) cudaFree(buf);
+    if (ubuf) cudaFree(ubuf);
+  }
 };
 
 namespace {
@@ -34,104 +42,96 @@ struct __align__(16) USlot {
   int rank;   // index among the unique keys
 };
 
-__global__ void unique_init_kernel(USlot* tab, unsigned long long cap, int* counts, long long n) {
-  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+// unique() keeps TWO scratch hash tables and alternates between them: the last kernel of a
+// call wipes the table the next call will use, so no call pays for a clearing pass on its
+// critical path.  Which table is current lives in device memory (sel[0]; sel[1] is the copy
+// the last kernel reads), not in host state, so the scheme survives CUDA-graph replay:
+// insert and rank read sel[0]; rank publishes sel[1] = sel[0]; index reads sel[1] and writes
+// sel[0] = sel[1] ^ 1.  No kernel writes a word that its own blocks read.
+struct UScratch {
+  USlot* tab[2];
+  unsigned long long* status[2];  // look-back words of the rank kernel, one per block
+  int* sel;
+  unsigned long long cap;  // slots per table (power of two)
+  int shift;               // 64 - log2(cap)
+  int nb_max;              // status words per table
+};
+
+__device__ __forceinline__ void wipe(USlot* tab, unsigned long long cap,
+                                     unsigned long long* status, int nb,
+                                     unsigned long long i, unsigned long long stride) {
   int4 e;
   e.x = 0; e.y = (int)0x80000000u; e.z = 0x7fffffff; e.w = 0;
   for (unsigned long long j = i; j < cap; j += stride) reinterpret_cast<int4*>(tab)[j] = e;
-  if (counts)
-    for (unsigned long long j = i; j < (unsigned long long)n; j += stride) counts[j] = 0;
+  for (unsigned long long j = i; j < (unsigned long long)nb; j += stride) status[j] = 0ULL;
 }
 
-__global__ void unique_insert_kernel(USlot* tab, unsigned long long mask, int shift,
-                                     const long long* __restrict__ ids, long long n,
-                                     int* __restrict__ slot_of) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__global__ void unique_wipe_kernel(UScratch s) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  wipe(s.tab[0], s.cap, s.status[0], s.nb_max, i, stride);
+  wipe(s.tab[1], s.cap, s.status[1], s.nb_max, i, stride);
+  if (i == 0) { s.sel[0] = 0; s.sel[1] = 0; }
+}
+
+// One probe per distinct id of a warp: the copies of a hot id inside a warp elect a leader
+// (match.any), so a Zipf head id costs one 64-bit CAS per warp instead of one per occurrence,
+// and the atomicMin is skipped once an earlier position is already recorded.
+__global__ void __launch_bounds__(256)
+unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
+                     int* __restrict__ slot_of, int* __restrict__ counts) {
+  USlot* tab = s.tab[s.sel[0] & 1];
+  const unsigned long long mask = s.cap - 1;
+  const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const long long key = ids[i];
-    // the sentinel itself is a legal id here: remap it onto a private slot key
-    unsigned long long pos = mix64((unsigned long long)key) >> shift;
-    for (;;) {
-      long long cur = __ldcg(&tab[pos].key);
-      if (cur == KEY_EMPTY) {
-        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[pos].key),
-                                           (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-        cur = old == (unsigned long long)KEY_EMPTY ? key : (long long)old;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n;
+       i0 += stride) {
+    const long long i = i0 + lane;
+    const bool valid = i < n;
+    const long long key = valid ? ids[i] : 0;
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    if (counts) counts[i] = 0;  // incremented two kernels later
+    const unsigned peers = __match_any_sync(active, key);
+    const int leader = __ffs(peers) - 1;  // lowest lane = smallest position
+    unsigned long long pos = 0;
+    if (lane == leader) {
+      pos = mix64((unsigned long long)key) >> s.shift;
+      for (;;) {
+        long long cur = __ldcg(&tab[pos].key);
+        if (cur == KEY_EMPTY) {
+          const unsigned long long old = atomicCAS(
+              reinterpret_cast<unsigned long long*>(&tab[pos].key),
+              (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+          cur = old == (unsigned long long)KEY_EMPTY ? key : (long long)old;
+        }
+        if (cur == key) break;
+        pos = (pos + 1) & mask;
       }
-      if (cur == key) break;
-      pos = (pos + 1) & mask;
+      if (__ldcg(&tab[pos].first) > (int)i) atomicMin(&tab[pos].first, (int)i);
     }
-    atomicMin(&tab[pos].first, (int)i);
+    pos = __shfl_sync(peers, pos, leader);
     slot_of[i] = (int)pos;
   }
 }
 
-__device__ __forceinline__ int block_sum(int v, int* sh) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int t = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-  __syncthreads();
-  return t;
-}
-
-// pass 1: number of first occurrences per block of UB ids
+// Ranks of the first occurrences in position order, in one pass: every block of UB ids
+// counts its first occurrences, publishes the count, and obtains the number of first
+// occurrences before it by decoupled look-back over the earlier blocks' status words
+// (flag 1 = block aggregate, flag 2 = inclusive prefix; value in the low 32 bits).
 __global__ void __launch_bounds__(256)
-unique_count_kernel(const USlot* __restrict__ tab, const int* __restrict__ slot_of, long long n,
-                    int* __restrict__ block_counts) {
-  __shared__ int sh[8];
-  const long long base = blockIdx.x * (long long)UB;
-  int c = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long i = base + k * 256 + threadIdx.x;
-    if (i < n) c += (tab[slot_of[i]].first == (int)i);
-  }
-  const int total = block_sum(c, sh);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-}
-
-// pass 2: exclusive scan of the block counts (one block)
-__global__ void __launch_bounds__(1024)
-unique_scan_kernel(int* __restrict__ block_counts, int nb, int* __restrict__ num_unique) {
-  __shared__ int sh[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nb; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < nb ? block_counts[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    const int incl = sh[threadIdx.x];
-    const int c0 = carry;
-    if (i < nb) block_counts[i] = c0 + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c0 + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *num_unique = carry;
-}
-
-// pass 3: rank of every first occurrence, in position order
-__global__ void __launch_bounds__(256)
-unique_assign_kernel(USlot* __restrict__ tab, const int* __restrict__ slot_of,
-                     const long long* __restrict__ ids, long long n,
-                     const int* __restrict__ block_offsets, long long* __restrict__ uniq) {
+unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
+                   const long long* __restrict__ ids, long long n,
+                   long long* __restrict__ uniq, int* __restrict__ num_unique) {
   __shared__ int warp_tot[8];
+  __shared__ int block_prefix;
+  const int which = sc.sel[0] & 1;
+  USlot* __restrict__ tab = sc.tab[which];
+  unsigned long long* status = sc.status[which];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc.sel[1] = which;
   const long long base = blockIdx.x * (long long)UB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // thread t owns 4 consecutive positions so that ranks follow position order
-  const long long i0 = base + threadIdx.x * 4;
+  const long long i0 = base + threadIdx.x * 4;  // 4 consecutive positions per thread
   int f[4], s[4];
   int c = 0;
 #pragma unroll
@@ -148,9 +148,38 @@ unique_assign_kernel(USlot* __restrict__ tab, const int* __restrict__ slot_of,
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < warp; ++w) woff += warp_tot[w];
-  int r = block_offsets[blockIdx.x] + woff + incl - c;
+  int woff = 0, total = 0;
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) woff += warp_tot[w];
+    total += warp_tot[w];
+  }
+  if (warp == 0) {
+    const int b = blockIdx.x;
+    volatile unsigned long long* st = status;
+    if (lane == 0)
+      st[b] = ((b == 0 ? 2ULL : 1ULL) << 32) | (unsigned int)total;
+    int prefix = 0;
+    for (int j = b - 1; j >= 0; j -= 32) {
+      const int idx = j - lane;
+      unsigned long long v = 2ULL << 32;  // lanes past block 0 act as a zero prefix
+      if (idx >= 0) {
+        do { v = st[idx]; } while ((v >> 32) == 0);
+      }
+      const unsigned done = __ballot_sync(0xffffffffu, (v >> 32) == 2);
+      const int stop = done ? __ffs(done) - 1 : 32;  // nearest block that has its prefix
+      int add = lane <= stop ? (int)(v & 0xffffffffULL) : 0;
+      for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+      prefix += add;
+      if (done) break;
+    }
+    if (lane == 0) {
+      if (b > 0) st[b] = (2ULL << 32) | (unsigned int)(prefix + total);
+      block_prefix = prefix;
+      if (b == (int)gridDim.x - 1) *num_unique = prefix + total;
+    }
+  }
+  __syncthreads();
+  int r = block_prefix + woff + incl - c;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (f[k]) {
@@ -161,15 +190,22 @@ unique_assign_kernel(USlot* __restrict__ tab, const int* __restrict__ slot_of,
   }
 }
 
-__global__ void unique_index_kernel(const USlot* __restrict__ tab, const int* __restrict__ slot_of,
-                                    long long n, int* __restrict__ idx, int* __restrict__ counts) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// idx[i] = rank of id i's slot; the same launch wipes the other table for the next call.
+__global__ void unique_index_kernel(UScratch s, const int* __restrict__ slot_of, long long n,
+                                    int* __restrict__ idx, int* __restrict__ counts) {
+  const int which = s.sel[1] & 1;
+  const USlot* __restrict__ tab = s.tab[which];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const int r = tab[slot_of[i]].rank;
-    idx[i] = r;
+  for (long long j = i; j < n; j += stride) {
+    const int r = tab[slot_of[j]].rank;
+    idx[j] = r;
     if (counts) atomicAdd(&counts[r], 1);
   }
+  // NB: the table just used stays dirty until the call after next wipes it
+  wipe(s.tab[which ^ 1], s.cap, s.status[which ^ 1], s.nb_max, (unsigned long long)i,
+       (unsigned long long)stride);
+  if (i == 0) s.sel[0] = which ^ 1;
 }
 
 // ---- UnsortedSegmentSum ----------------------------------------------------
@@ -192,75 +228,113 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
                : "memory");
 }
 
-// A block takes TILE consecutive rows of `data`.  Rows of the tile that share a
-// segment are first summed in shared memory (hot Zipf ids repeat thousands of
-// times per batch: without this every duplicate would be a same-address atomic
-// in L2), then each distinct segment of the tile is flushed once with
-// vectorised reductions.
+// A block takes TILE consecutive rows of `data` and issues their loads first.  While they
+// are in flight the rows' segment ids are hashed in shared memory, which tells every row
+// whether its segment occurs once in the tile (the common case: the row goes straight from
+// registers to the output with one vectorised reduction per 16 bytes) or several times (hot
+// Zipf ids repeat thousands of times per batch: those rows are staged in shared memory,
+// summed per segment by walking a per-segment row list, and flushed once — otherwise every
+// duplicate would be a same-address atomic in L2).
 template <int TILE>
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ data, const int* __restrict__ idx, long long n,
                    int dim, float* __restrict__ out) {
-  extern __shared__ __align__(16) float acc[];  // [TILE][dim]
-  __shared__ int seg[TILE];                     // segment id of local slot j
-  __shared__ int local_of[TILE];                // local slot of row r
-  __shared__ int htab[2 * TILE];                // open addressing: segment id -> local slot
+  extern __shared__ __align__(16) float stage[];  // [TILE][dim], only duplicate rows land here
+  __shared__ int seg[TILE];                       // segment id of local slot j
+  __shared__ int local_of[TILE];                  // local slot of row r
+  __shared__ int htab[2 * TILE];                  // open addressing: segment id -> local slot
   __shared__ int hval[2 * TILE];
+  __shared__ int head[TILE], nxt[TILE], cnt[TILE];
   __shared__ int n_local;
   const long long base = blockIdx.x * (long long)TILE;
   const int rows = (int)((n - base) < TILE ? (n - base) : TILE);
+  const int d4 = dim >> 2;
+  const bool vec = (dim & 3) == 0;
+  constexpr int PRE = 8;
+  float4 pre[PRE];
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+      const int e = threadIdx.x + k * 256;
+      if (e < rows * d4) {
+        const int r = e / d4, c = e - r * d4;
+        pre[k] = __ldcs(reinterpret_cast<const float4*>(data + (base + r) * dim) + c);
+      }
+    }
+  }
   for (int j = threadIdx.x; j < 2 * TILE; j += blockDim.x) htab[j] = -1;
+  for (int j = threadIdx.x; j < TILE; j += blockDim.x) { head[j] = -1; cnt[j] = 0; }
   if (threadIdx.x == 0) n_local = 0;
   __syncthreads();
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
     const int sgm = idx[base + r];
     unsigned h = ((unsigned)sgm * 2654435761u) & (2 * TILE - 1);
     for (;;) {
-      int cur = atomicCAS(&htab[h], -1, sgm);
+      const int cur = atomicCAS(&htab[h], -1, sgm);
       if (cur == -1) {
         const int j = atomicAdd(&n_local, 1);
         seg[j] = sgm;
-        // publish the local slot; losers spin on hval below
-        atomicExch(&hval[h], j + 1);
+        hval[h] = j;
         local_of[r] = j;
         break;
       }
-      if (cur == sgm) { local_of[r] = -(int)h - 1; break; }  // resolve after the barrier
+      if (cur == sgm) { local_of[r] = -(int)h - 1; break; }  // resolved after the barrier
       h = (h + 1) & (2 * TILE - 1);
     }
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < rows; r += blockDim.x)
-    if (local_of[r] < 0) local_of[r] = hval[-local_of[r] - 1] - 1;
-  const int nl = n_local;
-  const int d4 = dim >> 2;
-  const bool vec = (dim & 3) == 0;
-  for (int e = threadIdx.x; e < nl * dim; e += blockDim.x) acc[e] = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    int j = local_of[r];
+    if (j < 0) { j = hval[-j - 1]; local_of[r] = j; }
+    nxt[r] = atomicExch(&head[j], r);
+    atomicAdd(&cnt[j], 1);
+  }
   __syncthreads();
+  const int nl = n_local;
   if (vec) {
-    for (int e = threadIdx.x; e < rows * d4; e += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+      const int e = threadIdx.x + k * 256;
+      if (e < rows * d4) {
+        const int r = e / d4, c = e - r * d4;
+        const int j = local_of[r];
+        if (cnt[j] == 1) red_add_v4(out + (long long)seg[j] * dim + c * 4, pre[k]);
+        else *reinterpret_cast<float4*>(stage + r * dim + c * 4) = pre[k];
+      }
+    }
+    for (int e = threadIdx.x + PRE * 256; e < rows * d4; e += blockDim.x) {
       const int r = e / d4, c = e - r * d4;
+      const int j = local_of[r];
       const float4 v = __ldcs(reinterpret_cast<const float4*>(data + (base + r) * dim) + c);
-      float* a = acc + local_of[r] * dim + c * 4;
-      atomicAdd(a + 0, v.x); atomicAdd(a + 1, v.y); atomicAdd(a + 2, v.z); atomicAdd(a + 3, v.w);
+      if (cnt[j] == 1) red_add_v4(out + (long long)seg[j] * dim + c * 4, v);
+      else *reinterpret_cast<float4*>(stage + r * dim + c * 4) = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nl * d4; e += blockDim.x) {
+      const int j = e / d4, c = e - j * d4;
+      if (cnt[j] < 2) continue;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = head[j]; r >= 0; r = nxt[r]) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + r * dim + c * 4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      red_add_v4(out + (long long)seg[j] * dim + c * 4, a);
     }
   } else {
     for (int e = threadIdx.x; e < rows * dim; e += blockDim.x) {
       const int r = e / dim, c = e - r * dim;
-      atomicAdd(acc + local_of[r] * dim + c, __ldcs(data + (base + r) * dim + c));
+      const int j = local_of[r];
+      const float v = __ldcs(data + (base + r) * dim + c);
+      if (cnt[j] == 1) atomicAdd(out + (long long)seg[j] * dim + c, v);
+      else stage[r * dim + c] = v;
     }
-  }
-  __syncthreads();
-  if (vec) {
-    for (int e = threadIdx.x; e < nl * d4; e += blockDim.x) {
-      const int j = e / d4, c = e - j * d4;
-      const float4 v = *reinterpret_cast<const float4*>(acc + j * dim + c * 4);
-      red_add_v4(out + (long long)seg[j] * dim + c * 4, v);
-    }
-  } else {
+    __syncthreads();
     for (int e = threadIdx.x; e < nl * dim; e += blockDim.x) {
       const int j = e / dim, c = e - j * dim;
-      atomicAdd(out + (long long)seg[j] * dim + c, acc[e]);
+      if (cnt[j] < 2) continue;
+      float a = 0.f;
+      for (int r = head[j]; r >= 0; r = nxt[r]) a += stage[r * dim + c];
+      atomicAdd(out + (long long)seg[j] * dim + c, a);
     }
   }
 }
@@ -347,6 +421,9 @@ size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
 
+static bool ws_wiped(const Workspace* ws) { return ws->wiped_buf == ws->ubuf; }
+static void ws_mark_wiped(Workspace* ws) { ws->wiped_buf = ws->ubuf; }
+
 int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
               int32_t* counts, int32_t* num_unique, cudaStream_t st) {
   if (n < 0 || n > (1LL << 30)) return fail(1, "unique: n out of range");
@@ -356,30 +433,55 @@ int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32
   }
   unsigned long long cap = 1024;
   while (cap < (unsigned long long)n * 2) cap <<= 1;
-  int lg = 0;
-  while ((1ULL << lg) < cap) ++lg;
   const int nb = (int)((n + UB - 1) / UB);
-  const size_t b_tab = align_up(cap * sizeof(USlot));
-  const size_t b_slot = align_up((size_t)n * sizeof(int));
-  const size_t b_blk = align_up((size_t)nb * sizeof(int));
-  KV_TRY(ws->grab(b_tab + b_slot + b_blk, st));
-  char* p = static_cast<char*>(ws->buf);
-  USlot* tab = reinterpret_cast<USlot*>(p);
-  int* slot_of = reinterpret_cast<int*>(p + b_tab);
-  int* blk = reinterpret_cast<int*>(p + b_tab + b_slot);
-  const long long* k = reinterpret_cast<const long long*>(ids);
   const int dev = ws->device;
-  unique_init_kernel<<<blocks_for(cap, 256, dev), 256, 0, st>>>(tab, cap, counts, n);
+  if (cap > ws->ucap || nb > ws->unb) {  // (re)allocate and wipe both tables: rare, synchronises
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(2, "unique: scratch must be sized before CUDA-graph capture (run once eagerly)");
+    KV_CUDA(cudaStreamSynchronize(st));
+    if (ws->ubuf) cudaFree(ws->ubuf);
+    ws->ubuf = nullptr;
+    ws->wiped_buf = nullptr;
+    ws->ucap = cap > ws->ucap ? cap : ws->ucap;
+    ws->unb = nb > ws->unb ? nb : ws->unb;
+    const size_t b_tab = align_up(ws->ucap * sizeof(USlot));
+    const size_t b_st = align_up((size_t)ws->unb * sizeof(unsigned long long));
+    KV_CUDA(cudaMalloc(&ws->ubuf, 2 * (b_tab + b_st) + 256));
+  }
+  UScratch sc;
+  {
+    const size_t b_tab = align_up(ws->ucap * sizeof(USlot));
+    const size_t b_st = align_up((size_t)ws->unb * sizeof(unsigned long long));
+    char* p = static_cast<char*>(ws->ubuf);
+    sc.tab[0] = reinterpret_cast<USlot*>(p);
+    sc.tab[1] = reinterpret_cast<USlot*>(p + b_tab);
+    sc.status[0] = reinterpret_cast<unsigned long long*>(p + 2 * b_tab);
+    sc.status[1] = reinterpret_cast<unsigned long long*>(p + 2 * b_tab + b_st);
+    sc.sel = reinterpret_cast<int*>(p + 2 * (b_tab + b_st));
+    sc.cap = ws->ucap;
+    int lg = 0;
+    while ((1ULL << lg) < sc.cap) ++lg;
+    sc.shift = 64 - lg;
+    sc.nb_max = ws->unb;
+  }
+  static_assert(sizeof(UScratch) <= 64, "passed by value");
+  if (!ws->bytes || ws->bytes < align_up((size_t)n * sizeof(int))) KV_TRY(ws->grab(align_up((size_t)n * sizeof(int)), st));
+  int* slot_of = static_cast<int*>(ws->buf);
+  const long long* k = reinterpret_cast<const long long*>(ids);
+  if (ws->ubuf && !ws_wiped(ws)) {
+    unique_wipe_kernel<<<blocks_for(sc.cap, 256, dev), 256, 0, st>>>(sc);
+    KV_LAUNCHED();
+    ws_mark_wiped(ws);
+  }
+  unique_insert_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of, counts);
   KV_LAUNCHED();
-  unique_insert_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(tab, cap - 1, 64 - lg, k, n, slot_of);
+  unique_rank_kernel<<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
+                                         num_unique);
   KV_LAUNCHED();
-  unique_count_kernel<<<nb, 256, 0, st>>>(tab, slot_of, n, blk);
-  KV_LAUNCHED();
-  unique_scan_kernel<<<1, 1024, 0, st>>>(blk, nb, num_unique);
-  KV_LAUNCHED();
-  unique_assign_kernel<<<nb, 256, 0, st>>>(tab, slot_of, k, n, blk, reinterpret_cast<long long*>(uniq));
-  KV_LAUNCHED();
-  unique_index_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(tab, slot_of, n, idx, counts);
+  const long long span = n > (long long)sc.cap ? n : (long long)sc.cap;
+  unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx, counts);
   KV_LAUNCHED();
   return 0;
 }

@@ -6,13 +6,34 @@
 // 2, the warp moves the 32 rows cooperatively: a row is split over a tile of
 // `tpr` lanes doing 128-bit accesses, 32/tpr rows per step, four steps of loads
 // issued before the first store.
+#include <cstdlib>
+
 #include "table.h"
 
 namespace kvhbm {
 
+// Optional per-warp timeline for kernel tuning (scripts/trace_gather.py): when set, every
+// gather warp records {start ns, end ns, SM id, unused}.
+__device__ unsigned long long* g_trace = nullptr;
+int set_trace(unsigned long long* d_buf) {
+  KV_CUDA(cudaMemcpyToSymbol(g_trace, &d_buf, sizeof(d_buf)));
+  return 0;
+}
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+  return r;
+}
 
 // modes of a lane's id after phase 1
 constexpr int M_SKIP = -1;   // no output (padding lane / filtered id)
@@ -25,11 +46,13 @@ constexpr int M_CLAIM = 3;   // this lane inserted the key and must fill the row
 // KvVariable::FindOrInsert (kv_variable.h:263-380) when INSERT, else
 // KvVariable::FindOrZeros (kv_variable.h:239-254).
 // ---------------------------------------------------------------------------
-template <int VEC, int CPL, bool INSERT>
+template <int VEC, int CPL, bool INSERT, int UQ>
 __global__ void __launch_bounds__(256)
 gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
-              long long n, float* __restrict__ out, uint32_t today, int tpr) {
-  constexpr int UNR = CPL <= 2 ? 4 : (CPL == 4 ? 2 : 1);
+              long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags) {
+  // A warp takes `kpw` ids (lanes < kpw probe): small kpw = more warps, so the machine is
+  // full even for a 64 K-id batch and instruction latency hides behind other warps.
+  constexpr int UNR = UQ / CPL > 0 ? UQ / CPL : 1;  // rows in flight per lane
   const int lane = threadIdx.x & 31;
   const long long wpb = blockDim.x >> 5;
   const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -40,9 +63,17 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
   const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
   const int dim = t.dim;
 
-  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+  const int steps = kpw / kpi;  // row-movement steps per warp (kpw >= kpi)
+  __shared__ const float* s_src[8][32];
+  __shared__ signed char s_mode[8][32];
+  __shared__ unsigned char s_big[8][32];
+  const int wib = threadIdx.x >> 5;
+  unsigned long long* trace = g_trace;
+  unsigned long long t_start = 0, t_probe = 0;
+  if (trace) t_start = gtime();
+  for (long long base = warp0 * kpw; base < n; base += nwarps * kpw) {
     const long long i = base + lane;
-    const bool valid = i < n;
+    const bool valid = lane < kpw && i < n;
     const long long key = valid ? ids[i] : 0;
     int mode = M_SKIP;
     const float* src = nullptr;
@@ -78,9 +109,13 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
       }
     }
 
-    if (INSERT) {
-      // find_func / insert_func frequency bookkeeping, kv_variable.h:323-350,
-      // aggregated over the duplicates inside this warp.
+    if (trace) t_probe = gtime();
+    // find_func / insert_func frequency bookkeeping (kv_variable.h:323-350), aggregated over
+    // the duplicates inside this warp.  The atomic is issued now and its result is consumed
+    // after the rows have been moved, so its round trip overlaps the row traffic.
+    bool f_lead = false;
+    uint32_t f_cnt = 0, f_old = 0;
+    if (INSERT && !(flags & 1)) {
       const bool has = valid && pos >= 0;
       const unsigned active = __ballot_sync(FULL, has);
       if (has) {
@@ -89,23 +124,31 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         uint32_t sum = 0;
         for (unsigned p = peers; p; p &= p - 1)
           sum += __shfl_sync(peers, cnt, __ffs(p) - 1);
-        if (lane == __ffs(peers) - 1)
-          add_frequency(&t.slots[pos].freq, sum < 0xFFFFu ? sum : 0xFFFFu, today);
+        if (lane == __ffs(peers) - 1) {
+          f_lead = true;
+          f_cnt = sum < 0xFFFFu ? sum : 0xFFFFu;
+          f_old = atomicAdd(&t.slots[pos].freq, f_cnt << 16);
+        }
       }
     }
 
     // ---- cooperative row movement ----
-    bool my_under = (ctl & CTL_UNDER) != 0;
-    for (int it = 0; it < tpr; it += UNR) {
+    // Row pointers and modes go through shared memory (one broadcast LDS per row) instead of
+    // warp shuffles: with only a few warps per scheduler the dependent shuffle chains, not
+    // memory, were what a warp spent its time on.
+    s_src[wib][lane] = src;
+    s_mode[wib][lane] = (signed char)mode;
+    __syncwarp();
+    for (int it = 0; it < steps; it += UNR) {
       Chunk<VEC> c[UNR][CPL];
       int m[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         m[u] = M_SKIP;
-        if (it + u < tpr) {
+        if (it + u < steps) {
           const int kl = (it + u) * kpi + tq;
-          m[u] = __shfl_sync(FULL, mode, kl);
-          const float* sp = shfl_ptr(src, kl);
+          m[u] = s_mode[wib][kl];
+          const float* sp = s_src[wib][kl];
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             const int off = (q * tpr + tl) * VEC;
@@ -116,7 +159,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        if (it + u < tpr) {
+        if (it + u < steps) {
           const int kl = (it + u) * kpi + tq;
           bool big = false;
           float* op = out + (base + kl) * (long long)dim;
@@ -127,19 +170,21 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
             big |= chunk_over_cutoff(c[u][q], DEFAULT_CUTOFF);
           }
           if (INSERT) {
-            // UpdateUnderThreshold on a hit (kv_variable.h:329): the owner lane
-            // of each row picks its tile's verdict out of the ballot.
+            // UpdateUnderThreshold on a hit (kv_variable.h:329): the tile's verdict
             const unsigned bal = __ballot_sync(FULL, big);
-            if (lane / kpi == it + u)
-              my_under = ((bal >> ((lane % kpi) * tpr)) & tmask) == 0;
+            if (tl == 0) s_big[wib][kl] = ((bal >> (tq * tpr)) & tmask) != 0;
           }
         }
       }
     }
+    __syncwarp();
+    const bool my_under = INSERT ? !s_big[wib][lane] : false;
+    __syncwarp();
     if (INSERT && mode == M_COPY && my_under != ((ctl & CTL_UNDER) != 0)) {
       if (my_under) atomicOr(&t.slots[pos].ctl, CTL_UNDER);
       else atomicAnd(&t.slots[pos].ctl, ~CTL_UNDER);
     }
+    if (INSERT && f_lead) finish_frequency(&t.slots[pos].freq, f_old, f_cnt, today);
 
     if (INSERT) {
       // New keys (rare after warm-up): the whole warp builds one row at a time.
@@ -172,6 +217,10 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         }
       }
     }
+  }
+  if (trace && lane == 0) {
+    unsigned long long* r = trace + warp0 * 4;
+    r[0] = t_start; r[1] = gtime(); r[2] = smid(); r[3] = t_probe;
   }
 }
 
@@ -404,12 +453,24 @@ __global__ void permute_rows_kernel(const float* __restrict__ src, const int* __
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
                   float* out, uint16_t today, cudaStream_t st, int tpr) {
-  const int blocks = blocks_for(n, 256, tb->device);
+  static const int uq = getenv("KVHBM_GATHER_UQ") ? atoi(getenv("KVHBM_GATHER_UQ")) : 16;
+  static const int bs = getenv("KVHBM_GATHER_BS") ? atoi(getenv("KVHBM_GATHER_BS")) : 128;
+  static const int flags = getenv("KVHBM_GATHER_FLAGS") ? atoi(getenv("KVHBM_GATHER_FLAGS")) : 0;
+  static const int kpw_env = getenv("KVHBM_GATHER_KPW") ? atoi(getenv("KVHBM_GATHER_KPW")) : 0;
+  // ids per warp: the smallest power of two (>= rows per step) that still leaves at most
+  // ~48 warps per SM, so small batches spread over the whole chip
+  const int kpi = 32 / tpr;
+  int kpw = kpi;
+  const long long max_warps = (long long)sm_count(tb->device) * 48;
+  while (kpw < 32 && (n + kpw - 1) / kpw > max_warps) kpw <<= 1;
+  if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
+  const long long warps = (n + kpw - 1) / kpw;
+  const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const long long* k = reinterpret_cast<const long long*>(ids);
-  if (insert)
-    gather_kernel<VEC, CPL, true><<<blocks, 256, 0, st>>>(tb->view(), k, counts, n, out, today, tpr);
-  else
-    gather_kernel<VEC, CPL, false><<<blocks, 256, 0, st>>>(tb->view(), k, counts, n, out, today, tpr);
+#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags)
+  if (insert) { if (uq == 4) KV_G(true, 4); else if (uq == 8) KV_G(true, 8); else KV_G(true, 16); }
+  else { if (uq == 4) KV_G(false, 4); else if (uq == 8) KV_G(false, 8); else KV_G(false, 16); }
+#undef KV_G
   KV_LAUNCHED();
   return 0;
 }

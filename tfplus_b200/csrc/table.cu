@@ -207,7 +207,7 @@ __global__ void rehash_kernel(const Slot* old_slots, unsigned long long old_cap,
   for (; i < old_cap; i += stride) {
     Slot s = load_slot(old_slots + i);
     if (s.key == KEY_EMPTY || s.key == KEY_TOMB) continue;
-    unsigned long long pos = home_slot(nt, s.key);
+    unsigned long long pos = home_bucket(nt, s.key) * 2;
     for (;;) {
       unsigned long long old = atomicCAS(
           reinterpret_cast<unsigned long long*>(&nt.slots[pos].key),
@@ -276,7 +276,7 @@ TableView Table::view() const {
   v.mask = capacity - 1;
   int lg = 0;
   while ((1ULL << lg) < capacity) ++lg;
-  v.shift = 64 - lg;
+  v.shift = 64 - (lg - 1);
   v.rows = static_cast<float*>(arena.base());
   v.dim = dim;
   v.row_stride = row_stride;
