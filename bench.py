@@ -303,6 +303,10 @@ def main_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
     ab = algorithmic_bytes(B, u_meas, D)
+    if world > 1:
+      # every rank does the single-GPU step's table traffic on its shard
+      ab = {"step": sum(ab.values()) * world}
+      stage_ms = dict(stage_ms, step=ms / K)
     kern = {}
     for name, t_ms in stage_ms.items():
       if name in ab and t_ms > 0:
@@ -328,6 +332,14 @@ def main_ours(args):
                 "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K},
         "roofline": roof,
     }
+    if world > 1:
+      sent = stepper.tbl.router.bytes_sent / max(1, stepper.steps_done)
+      line["nvlink"] = {"bytes_sent_per_gpu_per_step": sent,
+                        "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
+                        "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
+                        "exchanges_per_step": 5,
+                        "note": "all_to_all: counts, ids, occurrence counts, rows, gradients"}
+      line["stage_ms"] = stage_ms
     if world == 1 and not args.no_cpu:
       cores = os.cpu_count() or 1
       cs = max(3, min(20, K))

@@ -14,7 +14,7 @@ HEADERS = ["common.cuh", "table.h", os.path.join("..", "..", "include", "kvhbm.h
 # and optimizer parity is stated in ulps of separately rounded fp32 ops.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static",
+    "-fmad=false", "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static",
 ]
 
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
   if failed:
     raise RuntimeError("libkvhbm build failed")
   if force or procs or _stale(LIB, objs):
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + [
+    cmd = [nvcc, "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o", LIB] + objs + [
         "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
   return LIB

@@ -10,6 +10,8 @@
 // contraction (this file is compiled with -fmad=false; sqrtf and `/` are the
 // IEEE-rounded versions).  Only the L2-norm reduction order differs (a tile
 // butterfly instead of Eigen's packet reduction).
+#include <cstdlib>
+
 #include "table.h"
 
 namespace kvhbm {
@@ -79,9 +81,17 @@ __host__ __device__ __forceinline__ ApplyParams derive_params(const float* hp, i
   return p;
 }
 
+extern __device__ unsigned long long* g_trace;  // lookup.cu: optional per-warp timeline
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned long long gtime_a() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int V_SKIP = -1;   // low-frequency key or padding: nothing happens
 constexpr int V_ZERO = 0;    // blacklisted key revived at zeros (table_manager.h:359-372)
@@ -134,41 +144,167 @@ __device__ __forceinline__ int resolve_slot_table(const TableView& t, long long 
   return V_COPY;
 }
 
-// A tile of `tpr` lanes owns one id: its leader probes the value table and the slot table(s)
-// at the same time (independent loads in flight together), the tile then reads gradient +
-// value + slots once with 128-bit accesses, updates them in registers and writes them back.
-// 32 / tpr ids per warp keep enough warps resident to hide the IEEE sqrt / divide chains.
+// Row math of one id, shared by every optimizer.  g/w/s are the tile's register copies of the
+// gradient, the value row and the slot parts; on return they hold the updated rows.  Returns
+// the blacklist verdict (group lasso only) and the tile-local "some |x| >= cutoff" flags.
 template <int VEC, int CPL, int KIND>
+__device__ __forceinline__ void row_update(const ApplyParams& p, int dim, int tpr, int vm,
+                                           Chunk<VEC> (&g)[CPL], Chunk<VEC> (&w)[CPL],
+                                           Chunk<VEC> (&s)[Kind<KIND>::PARTS][CPL], bool* vbig,
+                                           bool* abig, bool* bbig, bool* black) {
+  *vbig = *abig = *bbig = *black = false;
+  if (KIND == K_ADAGRAD) {
+    // training_ops.cc:1473-1482.  Under-threshold flags are those of the insert
+    // (kv_variable.h:398), Adagrad never refreshes them.
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      *vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+      *abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float gg = g[q].v[e];
+        float a = s[0][q].v[e];
+        if (p.update_slots) a += gg * gg;
+        s[0][q].v[e] = a;
+        if (dim > 1) w[q].v[e] -= (p.lr * gg) * (1.0f / sqrtf(a));
+        else w[q].v[e] -= (p.lr * gg) / sqrtf(a);
+      }
+    }
+  } else if (KIND == K_ADAM) {
+    // python/training/adam.py:116-156, every TF op rounded on its own
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float gg = g[q].v[e];
+        const float m_t = (s[0][q].v[e] * p.beta1) + (gg * p.one_minus_beta1);
+        const float v_t = (s[1][q].v[e] * p.beta2) + ((gg * gg) * p.one_minus_beta2);
+        s[0][q].v[e] = m_t;
+        s[1][q].v[e] = v_t;
+        if (vm != V_KEEP) w[q].v[e] -= (p.alpha * m_t) / (sqrtf(v_t) + p.epsilon);
+      }
+      *vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+      *abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
+               chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
+    }
+  } else {
+    // GroupAdam v4 (training_ops.cc:7166-7195) / SparseGroupFtrl (:713-751)
+    Chunk<VEC> z[CPL], den[CPL], gs[CPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float gg = g[q].v[e];
+        const float wv = w[q].v[e];
+        float lin;
+        if (KIND == K_GROUP_ADAM) {
+          const float m = p.beta1 * s[0][q].v[e] + p.one_minus_beta1 * gg;
+          const float vo = s[1][q].v[e];
+          const float nv = p.beta2 * vo + p.one_minus_beta2 * (gg * gg);
+          const float sq = sqrtf(nv);
+          lin = s[2][q].v[e];
+          if (p.later_step) lin += p.alpha * m - (sq - sqrtf(vo)) * wv;
+          else lin += p.alpha * m - (sq + p.epsilon) * wv;
+          s[0][q].v[e] = m;
+          s[1][q].v[e] = nv;
+          s[2][q].v[e] = lin;
+          den[q].v[e] = sq + p.epsilon + p.l2x2;
+          gs[q].v[e] = 0.f;
+        } else {
+          const float a = s[0][q].v[e];
+          const float gsh = gg + p.shrink2 * wv;
+          const float na = a + gsh * gsh;
+          const float pna = powp(p, na);
+          lin = s[1][q].v[e];
+          lin += gsh - (pna - powp(p, a)) / p.lr * wv;
+          s[1][q].v[e] = lin;
+          gs[q].v[e] = gsh;
+          den[q].v[e] = pna / p.lr + p.l2x2;
+        }
+        const float zz = clip_l1(lin, p.l1) - lin;
+        z[q].v[e] = zz;
+        ss += zz * zz;
+      }
+    }
+    for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+    const float nrm = sqrtf(ss);
+    *black = !(nrm > p.l21_norm);
+    const float c = 1.0f - p.l21_norm / nrm;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (!*black) w[q].v[e] = z[q].v[e] * c / den[q].v[e];
+        if (KIND == K_FTRL) {
+          // accum += grad_to_use.square(), re-evaluated with the new var (old var after a
+          // blacklist); see oracle/kv_oracle.cc
+          const float g2 = *black ? gs[q].v[e] : g[q].v[e] + p.shrink2 * w[q].v[e];
+          s[0][q].v[e] += g2 * g2;
+        }
+      }
+      *vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
+      if (KIND == K_GROUP_ADAM) {
+        *abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
+                 chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF) |
+                 chunk_over_cutoff(s[2][q], DEFAULT_CUTOFF);
+      } else {
+        *abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
+        *bbig |= chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
+      }
+    }
+  }
+}
+
+// The fused apply.  A warp takes `kpw` ids:
+//  phase 1, lanes < kpw, one id each: probe the value table and the slot table(s) at the same
+//           time (independent loads in flight together), claim missing keys, issue the slot
+//           frequency atomics, and leave row pointers + modes in shared memory;
+//  phase 2, tiles of `tpr` lanes: read gradient + value + slots of one id with 128-bit
+//           accesses (UNR ids in flight per tile), update in registers, write back once;
+//  phase 3, lanes < kpw: publish flags (under-threshold, blacklist) and finish the atomics.
+// kpw is chosen on the host so that one wave of warps covers the whole launch.
+template <int VEC, int CPL, int KIND, int UNR>
 __global__ void __launch_bounds__(128)
 apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restrict__ ids,
              const float* __restrict__ grad, long long n, const int* __restrict__ d_n,
-             ApplyParams p, const float* __restrict__ d_hp, uint32_t today, int tpr) {
+             ApplyParams p, const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw) {
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p.update_slots);
   constexpr int PARTS = Kind<KIND>::PARTS;
   constexpr bool TWO = Kind<KIND>::TWO;
+  __shared__ float* s_vp[4][32];
+  __shared__ float* s_ap[4][32];
+  __shared__ float* s_bp[4][32];
+  __shared__ long long s_key[4][32];
+  __shared__ int s_modes[4][32];          // vm | am << 8 | bm << 16 (each + 1, so SKIP = 0)
+  __shared__ unsigned char s_res[4][32];  // bit0 v_under, bit1 a_under, bit2 b_under, bit3 black
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const long long wpb = blockDim.x >> 5;
-  const int kpi = 32 / tpr;  // ids per warp
+  const int kpi = 32 / tpr;  // ids per tile round
   const int tl = lane & (tpr - 1);
   const int tq = lane / tpr;
-  const int leader = tq * tpr;
   const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int steps = kpw / kpi;
   const int dim = var.dim;
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
+  unsigned long long* trace = g_trace;
+  unsigned long long t0 = 0, t1 = 0, t2 = 0;
+  if (trace) t0 = gtime_a();
 
-  for (long long grp = blockIdx.x * wpb + (threadIdx.x >> 5); grp * kpi < n;
-       grp += (long long)gridDim.x * wpb) {
-    const long long i = grp * kpi + tq;
-    const bool valid = i < n;
+  for (long long base = (blockIdx.x * wpb + wib) * kpw; base < n;
+       base += (long long)gridDim.x * wpb * kpw) {
+    const long long i = base + lane;
+    const bool valid = lane < kpw && i < n;
 
-    // ---------------- phase 1: the tile leader resolves the id in every table ----------------
+    // ---------------- phase 1 ----------------
     long long key = 0;
     int vmode = V_SKIP, amode = V_SKIP, bmode = V_SKIP;
     long long vpos = -1, apos = -1, bpos = -1;
     uint32_t vctl = 0, actl = 0, bctl = 0;
     bool a_lead = false, b_lead = false;
     uint32_t a_old = 0, b_old = 0;
-    if (valid && tl == 0) {
+    if (valid) {
       key = ids[i];
       Probe pv = probe_begin(var, key), pa = probe_begin(sa, key), pb = probe_begin(sb, key);
       int rv = -1, ra = -1, rb = TWO ? -1 : 0;
@@ -212,176 +348,100 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
         if (amode == V_SKIP || (TWO && bmode == V_SKIP)) vmode = V_SKIP;
       }
     }
-    // hand the verdicts to the tile
-    const int vm = __shfl_sync(FULL, vmode, leader);
-    const int am = __shfl_sync(FULL, amode, leader);
-    const int bm = TWO ? __shfl_sync(FULL, bmode, leader) : V_SKIP;
-    const uint32_t vc = __shfl_sync(FULL, vctl, leader);
-    const uint32_t ac = __shfl_sync(FULL, actl, leader);
-    const uint32_t bc = TWO ? __shfl_sync(FULL, bctl, leader) : 0u;
-    const bool on = vm != V_SKIP;
-    float* vp = row_ptr(var, vc);
-    float* ap = row_ptr(sa, ac);
-    float* bp = row_ptr(sb, bc);
+    s_vp[wib][lane] = row_ptr(var, vctl);
+    s_ap[wib][lane] = row_ptr(sa, actl);
+    if (TWO) s_bp[wib][lane] = row_ptr(sb, bctl);
+    s_key[wib][lane] = key;
+    s_modes[wib][lane] = (vmode + 1) | ((amode + 1) << 8) | ((bmode + 1) << 16);
+    __syncwarp();
+    if (trace) t1 = gtime_a();
 
-    // ---------------- phase 2: the tile moves and updates the rows ----------------
-    Chunk<VEC> g[CPL], w[CPL], s[PARTS][CPL];
-    {
-      long long v1 = -1, v2 = -1, a1 = -1, a2 = -1, b1 = -1, b2 = -1;
-      if (__any_sync(FULL, vm == V_CLAIM || am == V_CLAIM || bm == V_CLAIM)) {
-        const long long k = shfl_ll(key, leader);
-        if (vm == V_CLAIM) init_rows_of(var, k, &v1, &v2);
-        if (am == V_CLAIM) init_rows_of(sa, k, &a1, &a2);
-        if (TWO && bm == V_CLAIM) init_rows_of(sb, k, &b1, &b2);
-      }
-      const float* gp = grad + i * (long long)dim;
+    // ---------------- phase 2 ----------------
+    for (int it = 0; it < steps; it += UNR) {
+      Chunk<VEC> g[UNR][CPL], w[UNR][CPL], s[UNR][PARTS][CPL];
+      int vm[UNR];
+      float *vp[UNR], *ap[UNR], *bp[UNR];
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const int off = (q * tpr + tl) * VEC;
-        const bool in = on && off < dim;
-        if (in) g[q].load_stream(gp + off); else chunk_zero(g[q]);
-        if (in && (vm == V_COPY || vm == V_KEEP)) w[q].load_cg(vp + off);
-        else if (in && vm == V_CLAIM) init_chunk<VEC>(var, v1, v2, off, w[q]);
-        else chunk_zero(w[q]);
-#pragma unroll
-        for (int r = 0; r < PARTS; ++r) {
-          const bool second = TWO && r == 1;
-          const int md = second ? bm : am;
-          float* rp = second ? bp : ap;
-          const int soff = (TWO ? 0 : r * dim) + off;
-          if (in && md == V_COPY) s[r][q].load_cg(rp + soff);
-          else if (in && md == V_CLAIM) {
-            if (second) init_chunk<VEC>(sb, b1, b2, soff, s[r][q]);
-            else init_chunk<VEC>(sa, a1, a2, soff, s[r][q]);
-          } else chunk_zero(s[r][q]);
-        }
-      }
-    }
-
-    bool vbig = false, abig = false, bbig = false, black = false;
-    if (KIND == K_ADAGRAD) {
-      // training_ops.cc:1473-1482.  Under-threshold flags are those of the insert
-      // (kv_variable.h:398), Adagrad never refreshes them.
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
-        abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float gg = g[q].v[e];
-          float a = s[0][q].v[e];
-          if (p.update_slots) a += gg * gg;
-          s[0][q].v[e] = a;
-          if (dim > 1) w[q].v[e] -= (p.lr * gg) * (1.0f / sqrtf(a));
-          else w[q].v[e] -= (p.lr * gg) / sqrtf(a);
-        }
-      }
-    } else if (KIND == K_ADAM) {
-      // python/training/adam.py:116-156, every TF op rounded on its own
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float gg = g[q].v[e];
-          const float m_t = (s[0][q].v[e] * p.beta1) + (gg * p.one_minus_beta1);
-          const float v_t = (s[1][q].v[e] * p.beta2) + ((gg * gg) * p.one_minus_beta2);
-          s[0][q].v[e] = m_t;
-          s[1][q].v[e] = v_t;
-          if (vm != V_KEEP) w[q].v[e] -= (p.alpha * m_t) / (sqrtf(v_t) + p.epsilon);
-        }
-        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
-        abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
-                chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
-      }
-    } else {
-      // GroupAdam v4 (training_ops.cc:7166-7195) / SparseGroupFtrl (:713-751)
-      Chunk<VEC> z[CPL], den[CPL], gs[CPL];
-      float ss = 0.f;
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float gg = g[q].v[e];
-          const float wv = w[q].v[e];
-          float lin;
-          if (KIND == K_GROUP_ADAM) {
-            const float m = p.beta1 * s[0][q].v[e] + p.one_minus_beta1 * gg;
-            const float vo = s[1][q].v[e];
-            const float nv = p.beta2 * vo + p.one_minus_beta2 * (gg * gg);
-            const float sq = sqrtf(nv);
-            lin = s[2][q].v[e];
-            if (p.later_step) lin += p.alpha * m - (sq - sqrtf(vo)) * wv;
-            else lin += p.alpha * m - (sq + p.epsilon) * wv;
-            s[0][q].v[e] = m;
-            s[1][q].v[e] = nv;
-            s[2][q].v[e] = lin;
-            den[q].v[e] = sq + p.epsilon + p.l2x2;
-            gs[q].v[e] = 0.f;
-          } else {
-            const float a = s[0][q].v[e];
-            const float gsh = gg + p.shrink2 * wv;
-            const float na = a + gsh * gsh;
-            const float pna = powp(p, na);
-            lin = s[1][q].v[e];
-            lin += gsh - (pna - powp(p, a)) / p.lr * wv;
-            s[1][q].v[e] = lin;
-            gs[q].v[e] = gsh;
-            den[q].v[e] = pna / p.lr + p.l2x2;
+      for (int u = 0; u < UNR; ++u) {
+        vm[u] = V_SKIP;
+        vp[u] = ap[u] = bp[u] = nullptr;
+        if (it + u < steps) {
+          const int kl = (it + u) * kpi + tq;
+          const int modes = s_modes[wib][kl];
+          vm[u] = (modes & 0xff) - 1;
+          const int am = ((modes >> 8) & 0xff) - 1;
+          const int bm = ((modes >> 16) & 0xff) - 1;
+          vp[u] = s_vp[wib][kl];
+          ap[u] = s_ap[wib][kl];
+          if (TWO) bp[u] = s_bp[wib][kl];
+          const bool on = vm[u] != V_SKIP;
+          long long v1 = -1, v2 = -1, a1 = -1, a2 = -1, b1 = -1, b2 = -1;
+          if (vm[u] == V_CLAIM || am == V_CLAIM || bm == V_CLAIM) {
+            const long long k = s_key[wib][kl];
+            if (vm[u] == V_CLAIM) init_rows_of(var, k, &v1, &v2);
+            if (am == V_CLAIM) init_rows_of(sa, k, &a1, &a2);
+            if (TWO && bm == V_CLAIM) init_rows_of(sb, k, &b1, &b2);
           }
-          const float zz = clip_l1(lin, p.l1) - lin;
-          z[q].v[e] = zz;
-          ss += zz * zz;
-        }
-      }
-      for (int o = tpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
-      const float nrm = sqrtf(ss);
-      black = !(nrm > p.l21_norm);
-      const float c = 1.0f - p.l21_norm / nrm;
+          const float* gp = grad + (base + kl) * (long long)dim;
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            const bool in = on && off < dim;
+            if (in) g[u][q].load_stream(gp + off); else chunk_zero(g[u][q]);
+            if (in && (vm[u] == V_COPY || vm[u] == V_KEEP)) w[u][q].load_cg(vp[u] + off);
+            else if (in && vm[u] == V_CLAIM) init_chunk<VEC>(var, v1, v2, off, w[u][q]);
+            else chunk_zero(w[u][q]);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          if (!black) w[q].v[e] = z[q].v[e] * c / den[q].v[e];
-          if (KIND == K_FTRL) {
-            // accum += grad_to_use.square(), re-evaluated with the new var (old var after
-            // a blacklist); see oracle/kv_oracle.cc
-            const float g2 = black ? gs[q].v[e] : g[q].v[e] + p.shrink2 * w[q].v[e];
-            s[0][q].v[e] += g2 * g2;
+            for (int r = 0; r < PARTS; ++r) {
+              const bool second = TWO && r == 1;
+              const int md = second ? bm : am;
+              float* rp = second ? bp[u] : ap[u];
+              const int soff = (TWO ? 0 : r * dim) + off;
+              if (in && md == V_COPY) s[u][r][q].load_cg(rp + soff);
+              else if (in && md == V_CLAIM) {
+                if (second) init_chunk<VEC>(sb, b1, b2, soff, s[u][r][q]);
+                else init_chunk<VEC>(sa, a1, a2, soff, s[u][r][q]);
+              } else chunk_zero(s[u][r][q]);
+            }
           }
         }
-        vbig |= chunk_over_cutoff(w[q], DEFAULT_CUTOFF);
-        if (KIND == K_GROUP_ADAM) {
-          abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF) |
-                  chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF) |
-                  chunk_over_cutoff(s[2][q], DEFAULT_CUTOFF);
-        } else {
-          abig |= chunk_over_cutoff(s[0][q], DEFAULT_CUTOFF);
-          bbig |= chunk_over_cutoff(s[1][q], DEFAULT_CUTOFF);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (it + u >= steps) continue;  // uniform across the warp
+        const int kl = (it + u) * kpi + tq;
+        const bool on = vm[u] != V_SKIP;
+        bool vbig, abig, bbig, black;
+        row_update<VEC, CPL, KIND>(p, dim, tpr, vm[u], g[u], w[u], s[u], &vbig, &abig, &bbig, &black);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (on && off < dim) {
+            if (vm[u] != V_KEEP) w[u][q].store(vp[u] + off);
+#pragma unroll
+            for (int r = 0; r < PARTS; ++r) {
+              const bool second = TWO && r == 1;
+              float* rp = second ? bp[u] : ap[u];
+              s[u][r][q].store(rp + (TWO ? 0 : r * dim) + off);
+            }
+          }
         }
+        const int sh = tq * tpr;
+        const unsigned vb = __ballot_sync(FULL, vbig);
+        const unsigned ab = __ballot_sync(FULL, abig);
+        const unsigned bb = TWO ? __ballot_sync(FULL, bbig) : 0u;
+        if (tl == 0)
+          s_res[wib][kl] = (((vb >> sh) & tmask) == 0 ? 1 : 0) | (((ab >> sh) & tmask) == 0 ? 2 : 0) |
+                           (((bb >> sh) & tmask) == 0 ? 4 : 0) | (black ? 8 : 0);
       }
     }
+    __syncwarp();
+    if (trace) t2 = gtime_a();
 
-    // write back
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-      const int off = (q * tpr + tl) * VEC;
-      if (on && off < dim) {
-        if (vm != V_KEEP) w[q].store(vp + off);
-#pragma unroll
-        for (int r = 0; r < PARTS; ++r) {
-          const bool second = TWO && r == 1;
-          float* rp = second ? bp : ap;
-          s[r][q].store(rp + (TWO ? 0 : r * dim) + off);
-        }
-      }
-    }
-    const int sh = tq * tpr;
-    const bool v_under = ((__ballot_sync(FULL, vbig) >> sh) & tmask) == 0;
-    const bool a_under = ((__ballot_sync(FULL, abig) >> sh) & tmask) == 0;
-    const bool b_under = TWO ? ((__ballot_sync(FULL, bbig) >> sh) & tmask) == 0 : false;
-
-    // ---------------- phase 3: the leader publishes flags ----------------
-    if (tl == 0 && vmode != V_SKIP) {
+    // ---------------- phase 3 ----------------
+    if (vmode != V_SKIP) {
+      const int res = s_res[wib][lane];
+      const bool v_under = res & 1, a_under = res & 2, b_under = res & 4, black = res & 8;
       uint32_t nv = CTL_READY | (vctl & CTL_ROW_MASK);
       if (KIND == K_ADAGRAD) {
         if (vmode == V_CLAIM) nv |= v_under ? CTL_UNDER : 0u;       // insert-time flag
@@ -409,6 +469,11 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
         if (b_lead) finish_frequency(&sb.slots[bpos].freq, b_old, 1u, today);
       }
     }
+    __syncwarp();
+  }
+  if (trace && lane == 0 && t1) {
+    unsigned long long* r = trace + (blockIdx.x * wpb + wib) * 4;
+    r[0] = t0; r[1] = gtime_a(); r[2] = t2; r[3] = t1;
   }
 }
 
@@ -416,13 +481,27 @@ template <int VEC, int CPL, int KIND>
 int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
                  int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
                  uint16_t today, cudaStream_t st, int tpr) {
+  static const int kpw_env = getenv("KVHBM_APPLY_KPW") ? atoi(getenv("KVHBM_APPLY_KPW")) : 0;
+  static const int unr_env = getenv("KVHBM_APPLY_UNR") ? atoi(getenv("KVHBM_APPLY_UNR")) : 0;
+  // ids per warp: the smallest power of two that keeps the launch within ~1.5 waves of warps
+  // (20 resident per SM at this register footprint); measured best on B200 (profiles/).  With
+  // d_n the launch is sized for the upper bound n; the usual caller (unique -> apply) has
+  // ~n/3 valid ids, hence the /2.
   const int kpi = 32 / tpr;
-  const int64_t warps = (n + kpi - 1) / kpi;
-  const int blocks = blocks_for(warps, 4, var->device, 16);
+  int kpw = kpi;
+  const long long max_warps = (long long)sm_count(var->device) * 32;
+  const long long n_est = d_n ? (n + 1) / 2 : n;
+  while (kpw < 32 && (n_est + kpw - 1) / kpw > max_warps) kpw <<= 1;
+  if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
+  const int64_t warps = (n + kpw - 1) / kpw;
+  const int blocks = blocks_for(warps, 4, var->device, 32);
   TableView vb = sb ? sb->view() : sa->view();
-  apply_kernel<VEC, CPL, KIND><<<blocks, 128, 0, st>>>(
-      var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,
-      d_hp, today, tpr);
+  const bool two = (CPL == 1) && unr_env == 2;
+#define KV_A(U) apply_kernel<VEC, CPL, KIND, U><<<blocks, 128, 0, st>>>(                          \
+      var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,     \
+      d_hp, today, tpr, kpw)
+  if (two) KV_A(2); else KV_A(1);
+#undef KV_A
   KV_LAUNCHED();
   return 0;
 }

@@ -453,15 +453,16 @@ __global__ void permute_rows_kernel(const float* __restrict__ src, const int* __
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
                   float* out, uint16_t today, cudaStream_t st, int tpr) {
-  static const int uq = getenv("KVHBM_GATHER_UQ") ? atoi(getenv("KVHBM_GATHER_UQ")) : 16;
+  static const int uq = getenv("KVHBM_GATHER_UQ") ? atoi(getenv("KVHBM_GATHER_UQ")) : 8;
   static const int bs = getenv("KVHBM_GATHER_BS") ? atoi(getenv("KVHBM_GATHER_BS")) : 128;
   static const int flags = getenv("KVHBM_GATHER_FLAGS") ? atoi(getenv("KVHBM_GATHER_FLAGS")) : 0;
   static const int kpw_env = getenv("KVHBM_GATHER_KPW") ? atoi(getenv("KVHBM_GATHER_KPW")) : 0;
-  // ids per warp: the smallest power of two (>= rows per step) that still leaves at most
-  // ~48 warps per SM, so small batches spread over the whole chip
+  // ids per warp: measured on B200, a 64 K-id batch is fastest with 32 ids per warp (one
+  // wave of ~14 warps per SM, 8 rows in flight per lane); smaller batches use fewer ids per
+  // warp so that they still spread over the whole chip
   const int kpi = 32 / tpr;
   int kpw = kpi;
-  const long long max_warps = (long long)sm_count(tb->device) * 48;
+  const long long max_warps = (long long)sm_count(tb->device) * 8;
   while (kpw < 32 && (n + kpw - 1) / kpw > max_warps) kpw <<= 1;
   if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
   const long long warps = (n + kpw - 1) / kpw;
