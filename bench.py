@@ -280,11 +280,13 @@ def main_ours(args):
   stepper.prepare_host(ids_h, grads_h, rows_h)
   for i in range(3):
     stepper.step_host(i)
+  stepper.finish_host()
   barrier()
   f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   f0.record()
   for i in range(K):
     stepper.step_host(i)
+  stepper.finish_host()
   f1.record()
   barrier()
   e2e_ms = f0.elapsed_time(f1)
@@ -386,6 +388,7 @@ class LocalStepper:
     self.graphs = {}
     self.overlap = os.environ.get("KVHBM_BENCH_OVERLAP", "1") != "0"
     self.side = torch.cuda.Stream(device=dev)
+    self.side2 = torch.cuda.Stream(device=dev)
 
   def populate(self):
     torch, ops = self.torch, self.ops
@@ -413,8 +416,11 @@ class LocalStepper:
       ws = ops.Workspace.get(self.dev)
       C(lib.kv_unique(ws.ptr, ids.data_ptr(), ids.numel(), buf["uniq"].data_ptr(),
                       buf["idx"].data_ptr(), None, buf["num"].data_ptr(), st))
+    elif name == "zero":
+      ops.zero_rows(buf["gsum"])
     elif name == "segment_sum":
-      ops.unsorted_segment_sum(grad, buf["idx"], buf["num"], out=buf["gsum"])
+      ops.unsorted_segment_sum(grad, buf["idx"], buf["num"], out=buf["gsum"],
+                               accumulate=self.overlap)
     elif name == "apply":
       ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, buf["gsum"], buf["uniq"],
                                                      self.hp, num_indices=buf["num"])
@@ -428,10 +434,15 @@ class LocalStepper:
       for name in self.STAGES:
         self.stage(name, ids, grad, buf)
       return buf["rows"]
+    # (the eager warm-up also goes through here, so the side streams exist before capture)
     main = torch.cuda.current_stream(self.dev)
     self.side.wait_stream(main)
+    self.side2.wait_stream(main)
+    with torch.cuda.stream(self.side2):
+      self.stage("zero", ids, grad, buf)       # the sums' destination, off the critical path
     with torch.cuda.stream(self.side):
       self.stage("unique", ids, grad, buf)
+      self.side.wait_stream(self.side2)
       self.stage("segment_sum", ids, grad, buf)
     self.stage("gather", ids, grad, buf)
     main.wait_stream(self.side)
@@ -461,9 +472,13 @@ class LocalStepper:
     self.ops.kv_variable_reserve(self.slot, 2 * self.batch)
     self.full = [self._capture(lambda i=i: self.step_eager(ids_d[i], grads_d[i], self.bufs[i]))
                  for i in range(len(ids_d))]
+    def one_stage(n, i):
+      if n == "segment_sum" and self.overlap:   # timed alone it includes its zeroing pass
+        self.stage("zero", ids_d[i], grads_d[i], self.bufs[i])
+      self.stage(n, ids_d[i], grads_d[i], self.bufs[i])
     self.stage_graphs = {
-        n: [self._capture(lambda i=i, n=n: self.stage(n, ids_d[i], grads_d[i], self.bufs[i]))
-            for i in range(len(ids_d))] for n in self.STAGES}
+        n: [self._capture(lambda i=i, n=n: one_stage(n, i)) for i in range(len(ids_d))]
+        for n in self.STAGES}
     self.torch.cuda.synchronize()
 
   def step(self, i):
@@ -490,23 +505,58 @@ class LocalStepper:
 
   # ---- end to end: pinned host buffers in, pinned host rows out ----
   def prepare_host(self, ids_h, grads_h, rows_h):
+    """End-to-end stepper: every step copies its ids + gradients from pinned host memory and
+    copies the gathered rows back.  The three legs run on three streams, double-buffered, so
+    the H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i (PCIe is full
+    duplex); every copy still happens, once per step, inside the timed region."""
     t = self.torch
-    self.h_ids = t.empty(self.batch, dtype=t.int64, device=self.dev)
-    self.h_grad = t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
-    self.h_buf = self.new_buffers()
-
-    def one(i):
-      self.h_ids.copy_(ids_h[i], non_blocking=True)
-      self.h_grad.copy_(grads_h[i], non_blocking=True)
-      rows = self.step_eager(self.h_ids, self.h_grad, self.h_buf)
-      rows_h.copy_(rows, non_blocking=True)
-
-    one(0)
+    self.ids_h, self.grads_h, self.rows_h = ids_h, grads_h, rows_h
+    self.s_h2d, self.s_d2h = t.cuda.Stream(device=self.dev), t.cuda.Stream(device=self.dev)
+    self.h_ids = [t.empty(self.batch, dtype=t.int64, device=self.dev) for _ in range(2)]
+    self.h_grad = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                   for _ in range(2)]
+    self.h_buf = [self.new_buffers() for _ in range(2)]
+    self.rows_host = [rows_h, t.empty_like(rows_h).pin_memory()]
+    self.ev_in = [t.cuda.Event() for _ in range(2)]     # inputs of slot k are on the device
+    self.ev_done = [t.cuda.Event() for _ in range(2)]   # kernels of slot k finished
+    self.ev_out = [t.cuda.Event() for _ in range(2)]    # rows of slot k reached the host
+    for k in range(2):
+      self.h_ids[k].copy_(ids_h[k])
+      self.h_grad[k].copy_(grads_h[k])
+      self.step_eager(self.h_ids[k], self.h_grad[k], self.h_buf[k])
     t.cuda.synchronize()
-    self.e2e = [self._capture(lambda i=i: one(i)) for i in range(len(ids_h))]
+    self.e2e = [self._capture(lambda k=k: self.step_eager(self.h_ids[k], self.h_grad[k],
+                                                          self.h_buf[k])) for k in range(2)]
+    main = t.cuda.current_stream(self.dev)
+    for k in range(2):
+      self.ev_done[k].record(main)
+      self.ev_out[k].record(main)
+    self.e2e_i = 0
 
   def step_host(self, i):
-    self.e2e[i % len(self.e2e)].replay()
+    t = self.torch
+    k = self.e2e_i & 1
+    self.e2e_i += 1
+    j = i % len(self.ids_h)
+    main = t.cuda.current_stream(self.dev)
+    with t.cuda.stream(self.s_h2d):
+      self.s_h2d.wait_event(self.ev_done[k])       # slot k's previous kernels no longer read it
+      self.h_ids[k].copy_(self.ids_h[j], non_blocking=True)
+      self.h_grad[k].copy_(self.grads_h[j], non_blocking=True)
+      self.ev_in[k].record(self.s_h2d)
+    main.wait_event(self.ev_in[k])
+    main.wait_event(self.ev_out[k])                # slot k's rows buffer has been drained
+    self.e2e[k].replay()
+    self.ev_done[k].record(main)
+    with t.cuda.stream(self.s_d2h):
+      self.s_d2h.wait_event(self.ev_done[k])
+      self.rows_host[k].copy_(self.h_buf[k]["rows"], non_blocking=True)
+      self.ev_out[k].record(self.s_d2h)
+
+  def finish_host(self):
+    main = self.torch.cuda.current_stream(self.dev)
+    main.wait_stream(self.s_h2d)
+    main.wait_stream(self.s_d2h)
 
 
 def main():

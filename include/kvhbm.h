@@ -182,10 +182,16 @@ int kv_unique(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq
               kv_stream stream);
 /* tf.math.unsorted_segment_sum(data[n, dim], idx, num_segments): d_out must
  * hold max_segments rows; rows [0, *d_num_segments) are written (all
- * max_segments rows when d_num_segments is NULL). */
+ * max_segments rows when d_num_segments is NULL).  With accumulate != 0 the
+ * sums are added to what d_out already holds (the caller zeroed it, e.g.
+ * with kv_zero_rows on another stream while the ids were being deduplicated). */
 int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx,
                    int64_t n, int dim, int64_t max_segments,
-                   const int32_t* d_num_segments, float* d_out, kv_stream stream);
+                   const int32_t* d_num_segments, float* d_out, int accumulate,
+                   kv_stream stream);
+/* d_out[0 .. min(max_rows, *d_num_rows)) [dim] = 0. */
+int kv_zero_rows(float* d_out, int64_t max_rows, const int32_t* d_num_rows, int dim,
+                 kv_stream stream);
 
 /* ---- checkpoint ---------------------------------------------------------- */
 

@@ -51,7 +51,8 @@ SIGNATURES = {
     "kv_workspace_create": [C.POINTER(vp)],
     "kv_workspace_destroy": [vp],
     "kv_unique": [vp, vp, i64, vp, vp, vp, vp, vp],
-    "kv_segment_sum": [vp, vp, vp, i64, i32, i64, vp, vp, vp],
+    "kv_segment_sum": [vp, vp, vp, i64, i32, i64, vp, vp, i32, vp],
+    "kv_zero_rows": [vp, i64, vp, i32, vp],
     "kv_export_count": [vp, i32, i32, f32, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
     "kv_export": [vp, i32, vp, vp, vp, vp, vp, i32, vp],
     "kv_import": [vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, vp],

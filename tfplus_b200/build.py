@@ -14,7 +14,7 @@ HEADERS = ["common.cuh", "table.h", os.path.join("..", "..", "include", "kvhbm.h
 # and optimizer parity is stated in ulps of separately rounded fp32 ops.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static",
+    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static",
 ]
 
 
@@ -33,8 +33,11 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-  """Compile every CUDA source and link the shared library.  Returns its path."""
+  """Compile every CUDA source and link the shared library.  Returns its path.
+  KVHBM_TRACE=1 in the environment compiles the per-warp timeline hooks used by
+  scripts/trace_*.py in (they cost registers, so they are off in the product build)."""
   nvcc = _nvcc()
+  extra = ["-DKVHBM_TRACE"] if os.environ.get("KVHBM_TRACE") == "1" else []
   hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
   objdir = os.path.join(HERE, "build")
   os.makedirs(objdir, exist_ok=True)
@@ -45,7 +48,7 @@ def build(force=False, verbose=False):
     o = os.path.join(objdir, src.replace(".cu", ".o"))
     objs.append(o)
     if force or _stale(o, [s] + hdrs):
-      cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+      cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
       procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
   failed = False
   for src, p in procs:

@@ -81,7 +81,12 @@ __host__ __device__ __forceinline__ ApplyParams derive_params(const float* hp, i
   return p;
 }
 
-extern __device__ unsigned long long* g_trace;  // lookup.cu: optional per-warp timeline
+// Optional per-warp timeline for kernel tuning (scripts/trace_apply.py).
+__device__ unsigned long long* g_trace_apply = nullptr;
+int set_trace_apply(unsigned long long* d_buf) {
+  KV_CUDA(cudaMemcpyToSymbol(g_trace_apply, &d_buf, sizeof(d_buf)));
+  return 0;
+}
 
 namespace {
 
@@ -288,9 +293,11 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
   const int steps = kpw / kpi;
   const int dim = var.dim;
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
-  unsigned long long* trace = g_trace;
+#ifdef KVHBM_TRACE
+  unsigned long long* trace = g_trace_apply;
   unsigned long long t0 = 0, t1 = 0, t2 = 0;
   if (trace) t0 = gtime_a();
+#endif
 
   for (long long base = (blockIdx.x * wpb + wib) * kpw; base < n;
        base += (long long)gridDim.x * wpb * kpw) {
@@ -354,7 +361,9 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
     s_key[wib][lane] = key;
     s_modes[wib][lane] = (vmode + 1) | ((amode + 1) << 8) | ((bmode + 1) << 16);
     __syncwarp();
+#ifdef KVHBM_TRACE
     if (trace) t1 = gtime_a();
+#endif
 
     // ---------------- phase 2 ----------------
     for (int it = 0; it < steps; it += UNR) {
@@ -436,7 +445,9 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
       }
     }
     __syncwarp();
+#ifdef KVHBM_TRACE
     if (trace) t2 = gtime_a();
+#endif
 
     // ---------------- phase 3 ----------------
     if (vmode != V_SKIP) {
@@ -471,10 +482,12 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
     }
     __syncwarp();
   }
+#ifdef KVHBM_TRACE
   if (trace && lane == 0 && t1) {
     unsigned long long* r = trace + (blockIdx.x * wpb + wib) * 4;
     r[0] = t0; r[1] = gtime_a(); r[2] = t2; r[3] = t1;
   }
+#endif
 }
 
 template <int VEC, int CPL, int KIND>

@@ -20,6 +20,8 @@ int do_insert(Table*, const int64_t*, const float*, int64_t, const uint8_t*, con
 int do_get_count(Table*, const int64_t*, int64_t, int32_t*, cudaStream_t);
 int do_get_timestamp(Table*, const int64_t*, int64_t, uint32_t*, uint16_t, cudaStream_t);
 int set_trace(unsigned long long* d_buf);
+int set_trace_apply(unsigned long long* d_buf);
+int set_trace_unique(unsigned long long* d_buf);
 int do_permute_rows(bool scatter, const float*, const int32_t*, int64_t, int, float*, cudaStream_t);
 
 int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
@@ -35,7 +37,8 @@ int do_apply_adam(Table*, Table*, const int64_t*, const float*, int64_t, const i
 int do_unique(Workspace*, const int64_t*, int64_t, int64_t*, int32_t*, int32_t*, int32_t*,
               cudaStream_t);
 int do_segment_sum(Workspace*, const float*, const int32_t*, int64_t, int, int64_t, const int32_t*,
-                   float*, cudaStream_t);
+                   float*, int accumulate, cudaStream_t);
+int do_zero_rows(float*, int64_t, const int32_t*, int, cudaStream_t);
 int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, int, int64_t*,
                      int32_t*, int32_t*, cudaStream_t);
 
@@ -333,11 +336,16 @@ int kv_unique(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq
 }
 int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx, int64_t n, int dim,
                    int64_t max_segments, const int32_t* d_num_segments, float* d_out,
-                   kv_stream stream) {
+                   int accumulate, kv_stream stream) {
   KV_NEED(ws && (n == 0 || (d_data && d_idx)) && (max_segments == 0 || d_out),
           "segment_sum: bad arguments");
   return do_segment_sum(ws->w, d_data, d_idx, n, dim, max_segments, d_num_segments, d_out,
-                        S(stream));
+                        accumulate, S(stream));
+}
+int kv_zero_rows(float* d_out, int64_t max_rows, const int32_t* d_num_rows, int dim,
+                 kv_stream stream) {
+  KV_NEED(max_rows == 0 || d_out, "zero_rows: bad arguments");
+  return do_zero_rows(d_out, max_rows, d_num_rows, dim, S(stream));
 }
 
 int kv_export_count(kv_table* t, int first_n, int enable_cutoff, float cutoff_value,
@@ -380,7 +388,11 @@ int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n, const in
   return do_partition_ids(ws->w, d_ids, n, d_n, num_shards, mode, d_sorted_ids, d_perm,
                           d_shard_counts, S(stream));
 }
-int kv_debug_set_trace(void* d_buf) { return set_trace(static_cast<unsigned long long*>(d_buf)); }
+int kv_debug_set_trace(void* d_buf) {
+  set_trace_apply(static_cast<unsigned long long*>(d_buf));
+  set_trace_unique(static_cast<unsigned long long*>(d_buf));
+  return set_trace(static_cast<unsigned long long*>(d_buf));
+}
 int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
                     kv_stream stream) {
   return do_permute_rows(false, d_src, d_perm, n, dim, d_out, S(stream));

@@ -32,6 +32,8 @@ struct Workspace {
   }
 };
 
+int set_trace_unique(unsigned long long*) { return 0; }
+
 namespace {
 
 constexpr int UB = 1024;  // ids per block in the scan kernels (256 threads x 4)
@@ -486,11 +488,21 @@ int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32
   return 0;
 }
 
+int do_zero_rows(float* out, int64_t max_rows, const int32_t* d_rows, int dim, cudaStream_t st) {
+  if (max_rows <= 0) return 0;
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  const int64_t work = max_rows * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
+  zero_rows_kernel<<<blocks_for(work, 256, dev, 16), 256, 0, st>>>(out, max_rows, d_rows, dim);
+  KV_LAUNCHED();
+  return 0;
+}
+
 int do_segment_sum(Workspace* ws, const float* data, const int32_t* idx, int64_t n, int dim,
                    int64_t max_segments, const int32_t* d_num_segments, float* out,
-                   cudaStream_t st) {
+                   int accumulate, cudaStream_t st) {
   if (dim <= 0) return fail(1, "segment_sum: dim must be positive");
-  if (max_segments > 0) {
+  if (max_segments > 0 && !accumulate) {
     const int64_t work = max_segments * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
     zero_rows_kernel<<<blocks_for(work, 256, ws->device, 16), 256, 0, st>>>(
         out, max_segments, d_num_segments, dim);

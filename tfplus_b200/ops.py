@@ -581,7 +581,15 @@ def unique_with_counts(x):
   return unique(x, with_counts=True)
 
 
-def unsorted_segment_sum(data, segment_ids, num_segments, out=None):
+def zero_rows(out, num_rows=None):
+  """out[:num_rows] = 0 (num_rows: None = all rows, or a 1-element int32 device tensor)."""
+  with torch.cuda.device(out.device):
+    check(_lib.load().kv_zero_rows(out.data_ptr(), out.shape[0], _ptr(num_rows),
+                                   out.numel() // max(1, out.shape[0]), _stream(out.device)))
+  return out
+
+
+def unsorted_segment_sum(data, segment_ids, num_segments, out=None, accumulate=False):
   """tf.math.unsorted_segment_sum; num_segments may be an int or a 1-element int32 device
   tensor (then `out` keeps data.shape[0] rows and only the first num_segments are defined)."""
   data = data.contiguous()
@@ -600,7 +608,8 @@ def unsorted_segment_sum(data, segment_ids, num_segments, out=None):
   ws = Workspace.get(dev)
   with torch.cuda.device(dev):
     check(_lib.load().kv_segment_sum(ws.ptr, data.data_ptr(), seg.data_ptr(), n, dim, max_seg,
-                                     _ptr(dnum), out.data_ptr(), _stream(dev)))
+                                     _ptr(dnum), out.data_ptr(), int(bool(accumulate)),
+                                     _stream(dev)))
   return out
 
 

@@ -242,6 +242,9 @@ class ShardedStepper:
     self.h_ids = t.empty(self.batch, dtype=t.int64, device=self.dev)
     self.h_grad = t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
 
+  def finish_host(self):
+    pass
+
   def step_host(self, i):
     k = i % len(self.ids_h)
     self.h_ids.copy_(self.ids_h[k], non_blocking=True)
