@@ -218,6 +218,12 @@ def main_ours(args):
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+  def note(msg):
+    if os.environ.get("KVHBM_BENCH_VERBOSE"):
+      sys.stderr.write("[rank %d] %s\n" % (rank, msg))
+      sys.stderr.flush()
+
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
                      "use --impl reference for the CPU arm")
@@ -234,7 +240,9 @@ def main_ours(args):
     stepper = sharded.ShardedStepper(keys, D, B, HP, dev, rank, world)
   else:
     stepper = LocalStepper(keys, D, B, dev)
+  note('created')
   stepper.populate()
+  note('populated')
 
   nb = N_BATCHES
   ids_np, grads_np = make_batches(nb, keys * world, B, D, seed_ids=2024 + rank,
@@ -250,6 +258,7 @@ def main_ours(args):
 
   # ---- warm-up + timed region (inputs resident in HBM) ----
   stepper.prepare(ids_d, grads_d)
+  note('prepared')
   for i in range(W):
     stepper.step(i)
   barrier()
@@ -271,7 +280,9 @@ def main_ours(args):
   value = B * world * K / (ms * 1e-3)
 
   # ---- per-stage device times (same steps, events between the stages) ----
+  note('timed %.3f ms/step' % (ms / K))
   stage_ms = stepper.stage_times(K)
+  note('stages')
 
   # ---- end to end: host buffers in, host rows out, copies inside the timed region ----
   ids_h = [torch.from_numpy(x).pin_memory() for x in ids_np]
@@ -295,6 +306,7 @@ def main_ours(args):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_ms = float(tt.item())
   e2e_val = B * world * K / (e2e_ms * 1e-3)
+  note('e2e')
 
   if rank == 0:
     peaks = {}
@@ -335,12 +347,14 @@ def main_ours(args):
         "roofline": roof,
     }
     if world > 1:
-      sent = stepper.tbl.router.bytes_sent / max(1, stepper.steps_done)
+      sent = stepper.padded.wire_bytes
       line["nvlink"] = {"bytes_sent_per_gpu_per_step": sent,
                         "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
                         "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
-                        "exchanges_per_step": 5,
-                        "note": "all_to_all: counts, ids, occurrence counts, rows, gradients"}
+                        "exchanges_per_step": 4, "capacity_per_peer": stepper.padded.cap,
+                        "overflowed": stepper.padded.overflowed(),
+                        "note": "fixed-capacity all_to_all of ids, occurrence counts, rows, "
+                                "gradients, captured with the kernels in one CUDA graph"}
       line["stage_ms"] = stage_ms
     if world == 1 and not args.no_cpu:
       cores = os.cpu_count() or 1
@@ -352,6 +366,9 @@ def main_ours(args):
                     "oracle port of the reference algorithm, %d threads" % (keys, cs, B, cores)}
     print(json.dumps(line))
   if world > 1:
+    stepper.release()      # captured NCCL work must be gone before the process group
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
   return 0
 

@@ -239,6 +239,24 @@ int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n,
                      const int32_t* d_n, int num_shards, int mode,
                      int64_t* d_sorted_ids, int32_t* d_perm, int32_t* d_shard_counts,
                      kv_stream stream);
+/* Fixed-capacity variant for a sync-free exchange: d_send_ids / d_send_occ are
+ * [num_shards][capacity]; the ids owned by shard g (and their occurrence
+ * counts d_occ, or 1) fill [g][0 .. d_counts[g]), the rest is padding
+ * (INT64_MIN+1, which lookups answer with zeros and applies skip).  d_perm[i]
+ * is the padded position of input i, or -1 if its shard row was full, in which
+ * case *d_overflow is set to 1 (it is never cleared here).  Nothing depends on
+ * the data, so the all-to-all that follows can be captured in a CUDA graph. */
+int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                 const int32_t* d_n, int num_shards, int mode, int capacity,
+                 int64_t* d_send_ids, int32_t* d_send_occ, int32_t* d_perm,
+                 int32_t* d_counts, int32_t* d_overflow, kv_stream stream);
+/* out[i, :] = src[perm[idx[i]], :]; perm and/or idx may be NULL (identity); a
+ * negative perm entry yields zeros. */
+int kv_expand_rows(const float* d_src, const int32_t* d_perm, const int32_t* d_idx, int64_t n,
+                   int dim, float* d_out, kv_stream stream);
+/* out[perm[i], :] = src[i, :] for i < min(n, *d_n); negative perm entries are skipped. */
+int kv_scatter_rows_n(const float* d_src, const int32_t* d_perm, int64_t n, const int32_t* d_n,
+                      int dim, float* d_out, kv_stream stream);
 /* out[i, :] = src[perm[i], :] (gather rows back into request order). */
 int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim,
                     float* d_out, kv_stream stream);

@@ -125,3 +125,146 @@ def test_two_nccl_ranks_equal_one_table():
   assert set(got_rows) == set(int(a) for a in ref["keys"])
   for a, b in zip(ref["keys"], ref["values"]):
     np.testing.assert_allclose(got_rows[int(a)], b, rtol=1e-6, atol=1e-7)
+
+
+PAD = -2**63 + 1
+
+
+def test_route_ids_padded_layout():
+  rng = np.random.default_rng(7)
+  ids = np.unique(rng.integers(-2**40, 2**40, size=6000).astype(np.int64))
+  occ = rng.integers(1, 9, size=ids.size).astype(np.int32)
+  G, cap = 4, 2048
+  num = torch.tensor([ids.size - 100], dtype=torch.int32, device=DEV)   # only a prefix is valid
+  r = ops.route_ids(t(ids), t(occ), G, cap, "hash", num_ids=num)
+  n = ids.size - 100
+  own = owner_of(ids[:n], G)
+  counts = r["counts"].cpu().numpy()
+  np.testing.assert_array_equal(counts, np.bincount(own, minlength=G))
+  send_ids = r["send_ids"].cpu().numpy().reshape(G, cap)
+  send_occ = r["send_occ"].cpu().numpy().reshape(G, cap)
+  perm = r["perm"].cpu().numpy()[:n]
+  assert int(r["overflow"].item()) == 0
+  for g in range(G):
+    assert set(send_ids[g, :counts[g]].tolist()) == set(ids[:n][own == g].tolist())
+    assert (send_ids[g, counts[g]:] == PAD).all() and (send_occ[g, counts[g]:] == 0).all()
+  np.testing.assert_array_equal(send_ids.reshape(-1)[perm], ids[:n])
+  np.testing.assert_array_equal(send_occ.reshape(-1)[perm], occ[:n])
+  # overflow: capacity too small is reported, nothing is written out of bounds
+  r2 = ops.route_ids(t(ids), t(occ), G, 64, "hash")
+  assert int(r2["overflow"].item()) == 1
+  assert (r2["perm"].cpu().numpy() < G * 64).all()
+
+
+def test_pad_ids_are_ignored_and_row_helpers():
+  p = Pair(16, init=0.5)
+  acc = Pair(16, init=0.1)
+  ids = np.array([5, PAD, 7, PAD], np.int64)
+  rows = ops.kv_variable_gather_or_insert_v2(p.gpu, t(ids)).cpu().numpy()
+  assert (rows[[1, 3]] == 0).all() and (rows[[0, 2]] == 0.5).all()
+  assert ops.kv_variable_shape_v2(p.gpu)[0] == 2
+  ops.kv_variable_sparse_apply_adagrad(p.gpu, acc.gpu, 0.1, torch.ones(3, 16, device=DEV),
+                                       t(np.array([5, PAD, 9], np.int64)))
+  assert ops.kv_variable_shape_v2(p.gpu)[0] == 3 and ops.kv_variable_shape_v2(acc.gpu)[0] == 2
+  src = torch.arange(40, dtype=torch.float32, device=DEV).reshape(10, 4)
+  perm = torch.tensor([9, -1, 0, 3], dtype=torch.int32, device=DEV)
+  idx = torch.tensor([3, 3, 0, 1, 2], dtype=torch.int32, device=DEV)
+  out = ops.expand_rows(src, perm, idx, 5, torch.empty(5, 4, device=DEV)).cpu().numpy()
+  np.testing.assert_array_equal(out, src.cpu().numpy()[[3, 3, 9, 0, 0]] * np.array([1, 1, 1, 0, 1])[:, None])
+  dst = torch.zeros(10, 4, device=DEV)
+  ops.scatter_rows_n(src[:4], perm, 4, torch.tensor([3], dtype=torch.int32, device=DEV), dst)
+  want = np.zeros((10, 4), np.float32)
+  want[9], want[0] = src[0].cpu().numpy(), src[2].cpu().numpy()
+  np.testing.assert_array_equal(dst.cpu().numpy(), want)
+
+
+def _padded_worker(rank, world, port, q, use_graph):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dev = torch.device("cuda", rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+  from tfplus_b200.sharded import PaddedShardedStep
+  ops.set_today(TODAY)
+  var = ops.kv_variable(value_shape=[D], enter_threshold=0, device=dev, seed=5, capacity_hint=4096)
+  slot = ops.kv_variable(value_shape=[3 * D], device=dev, seed=5, capacity_hint=4096)
+  ops.init_kv_variable_v2(var, torch.full((16, D), 0.5, device=dev))
+  ops.init_kv_variable_v2(slot, torch.zeros(16, 3 * D, device=dev))
+  hp = torch.tensor([0.05, 0.9, 0.999, 0.9, 0.999, 1e-8, 1e-5, 1e-5, 1e-5], device=dev)
+  betas = torch.tensor([0.9, 0.999], device=dev)
+  step = PaddedShardedStep(var, slot, D, 400, world, rank, dev, hp, betas, cap=256)
+  data = [batches(world, s) for s in range(3)]
+  ids = [torch.from_numpy(d[0][rank]).to(dev) for d in data]
+  grads = [torch.from_numpy(d[1][rank]).to(dev) for d in data]
+  looked = []
+  if use_graph:
+    step.run(ids[0], grads[0])            # eager warm-up = step 0
+    looked.append(step.out.cpu().numpy().copy())
+    torch.cuda.synchronize()
+    graphs = []
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      for s in (1, 2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+          step.run(ids[s], grads[s])
+        graphs.append(g)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for g in graphs:
+      g.replay()
+      torch.cuda.synchronize()
+      looked.append(step.out.cpu().numpy().copy())
+    del graphs, g          # captured NCCL work must be gone before the process group is torn down
+    torch.cuda.synchronize()
+  else:
+    for s in range(3):
+      looked.append(step.run(ids[s], grads[s]).cpu().numpy().copy())
+  assert not step.overflowed()
+  k, v, _, _, fk, fv = ops.kv_variable_export(var, first_n=6, enable_cutoff=True,
+                                              cutoff_value=1e-20, freq_dtype=torch.int32)
+  q.put((rank, looked, k.cpu().numpy(), v.cpu().numpy(), fk.cpu().numpy(),
+         fv.cpu().numpy().view(np.uint32)))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_padded_sharded_step_equals_one_table(use_graph):
+  world = 2
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_padded_worker, args=(r, world, port, q, use_graph)) for r in range(world)]
+  for p in procs:
+    p.start()
+  results = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  var = make_table(D, 0, 0.5)
+  slot = ob.OracleTable(3 * D, 0, seed=5)
+  slot.set_init_table(np.zeros((16, 3 * D), np.float32))
+  b1p, b2p = np.float32(0.9), np.float32(0.999)
+  for step in range(3):
+    ids_all, grads_all = batches(world, step)
+    ids, grad = np.concatenate(ids_all), np.concatenate(grads_all)
+    rows = var.gather_or_insert(ids, today=TODAY)
+    off = 0
+    for r in range(world):
+      n = ids_all[r].size
+      np.testing.assert_allclose(results[r][1][step], rows[off:off + n], rtol=1e-6, atol=1e-7)
+      off += n
+    u, idx = ob.unique(ids)
+    ob.apply_group_adam_v4(var, slot, u, ob.segment_sum(grad, idx, u.size), 0.05, float(b1p),
+                           float(b2p), 0.9, 0.999, 1e-8, 1e-5, 1e-5, 1e-5, today=TODAY)
+    b1p, b2p = b1p * np.float32(0.9), b2p * np.float32(0.999)
+  ref = var.export(first_n=6, enable_cutoff=True, cutoff_value=1e-20, freq_u32=True)
+  got_rows, got_freq = {}, {}
+  for _, _, k, v, fk, fv in results:
+    got_rows.update({int(a): b for a, b in zip(k, v)})
+    got_freq.update({int(a): int(b) for a, b in zip(fk, fv)})
+  assert got_freq == {int(a): int(b) for a, b in zip(ref["freq_keys"], ref["freq_values"])}
+  assert set(got_rows) == set(int(a) for a in ref["keys"])
+  for a, b in zip(ref["keys"], ref["values"]):
+    np.testing.assert_allclose(got_rows[int(a)], b, rtol=1e-6, atol=1e-7)

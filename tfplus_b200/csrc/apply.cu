@@ -311,8 +311,8 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
     uint32_t vctl = 0, actl = 0, bctl = 0;
     bool a_lead = false, b_lead = false;
     uint32_t a_old = 0, b_old = 0;
-    if (valid) {
-      key = ids[i];
+    if (valid) key = ids[i];
+    if (valid && key != KEY_PAD) {  // padding ids of the shard exchange are skipped
       Probe pv = probe_begin(var, key), pa = probe_begin(sa, key), pb = probe_begin(sb, key);
       int rv = -1, ra = -1, rb = TWO ? -1 : 0;
       Slot sv, ssa, ssb, x0, x1, y0, y1, z0, z1;

@@ -42,6 +42,11 @@ int do_zero_rows(float*, int64_t, const int32_t*, int, cudaStream_t);
 int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, int, int64_t*,
                      int32_t*, int32_t*, cudaStream_t);
 
+int do_route_ids(Workspace*, const int64_t*, const int32_t*, int64_t, const int32_t*, int, int, int,
+                 int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int do_expand_rows(const float*, const int32_t*, const int32_t*, int64_t, int, float*, cudaStream_t);
+int do_scatter_rows_n(const float*, const int32_t*, int64_t, const int32_t*, int, float*,
+                      cudaStream_t);
 int do_stats(Table*, cudaStream_t, int64_t*, int64_t*, int64_t*);
 int do_export_count(Table*, int, int, float, cudaStream_t, int64_t*, int64_t*, int64_t*);
 int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cudaStream_t);
@@ -392,6 +397,23 @@ int kv_debug_set_trace(void* d_buf) {
   set_trace_apply(static_cast<unsigned long long*>(d_buf));
   set_trace_unique(static_cast<unsigned long long*>(d_buf));
   return set_trace(static_cast<unsigned long long*>(d_buf));
+}
+int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                 const int32_t* d_n, int num_shards, int mode, int capacity, int64_t* d_send_ids,
+                 int32_t* d_send_occ, int32_t* d_perm, int32_t* d_counts, int32_t* d_overflow,
+                 kv_stream stream) {
+  KV_NEED(ws && d_send_ids && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
+          "route_ids: bad arguments");
+  return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_ids,
+                      d_send_occ, d_perm, d_counts, d_overflow, S(stream));
+}
+int kv_expand_rows(const float* d_src, const int32_t* d_perm, const int32_t* d_idx, int64_t n,
+                   int dim, float* d_out, kv_stream stream) {
+  return do_expand_rows(d_src, d_perm, d_idx, n, dim, d_out, S(stream));
+}
+int kv_scatter_rows_n(const float* d_src, const int32_t* d_perm, int64_t n, const int32_t* d_n,
+                      int dim, float* d_out, kv_stream stream) {
+  return do_scatter_rows_n(d_src, d_perm, n, d_n, dim, d_out, S(stream));
 }
 int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
                     kv_stream stream) {

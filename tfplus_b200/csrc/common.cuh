@@ -22,6 +22,9 @@ namespace kvhbm {
 
 constexpr long long KEY_EMPTY = (long long)0x8000000000000000ULL;
 constexpr long long KEY_TOMB = (long long)0x8000000000000001ULL;
+// Also the padding id of the fixed-capacity shard exchange: lookups of it return zeros, applies
+// skip it, nothing probes the table for it (kv_route_ids pads its send buffers with it).
+constexpr long long KEY_PAD = KEY_TOMB;
 
 constexpr uint32_t CTL_READY = 0x80000000u;  // row contents are published
 constexpr uint32_t CTL_BLACK = 0x40000000u;  // EmbeddingValue::in_black_

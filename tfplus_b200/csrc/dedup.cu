@@ -419,6 +419,67 @@ partition_scatter_kernel(const long long* __restrict__ ids, long long n, const i
   }
 }
 
+// ---- fixed-capacity routing: the sync-free variant of partition_ids -------------------------
+// send_ids / send_occ are [num_shards][cap]: the ids owned by shard g go to [g][0 .. count_g),
+// the rest of each row is padding (KEY_PAD / 0).  Shapes do not depend on the data, so the
+// exchange that follows needs no host synchronisation and can be captured in a CUDA graph.
+__global__ void route_fill_kernel(long long* send_ids, int* send_occ, long long total, int* counts,
+                                  int num_shards) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = i; j < total; j += stride) {
+    send_ids[j] = KEY_PAD;
+    if (send_occ) send_occ[j] = 0;
+  }
+  if (i < num_shards) counts[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ occ, long long n,
+                     const int* d_n, int num_shards, int mode, int cap,
+                     long long* __restrict__ send_ids, int* __restrict__ send_occ,
+                     int* __restrict__ perm, int* __restrict__ counts, int* __restrict__ overflow) {
+  __shared__ int hist[MAX_SHARDS];
+  __shared__ int basepos[MAX_SHARDS];
+  if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
+  const long long per_block = 256 * 8;
+  for (long long b0 = blockIdx.x * per_block; b0 < n; b0 += gridDim.x * per_block) {
+    for (int g = threadIdx.x; g < num_shards; g += blockDim.x) hist[g] = 0;
+    __syncthreads();
+    int own[8], lr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = b0 + k * 256 + threadIdx.x;
+      own[k] = -1;
+      if (i < n) {
+        own[k] = owner_of(ids[i], num_shards, mode);
+        lr[k] = atomicAdd(&hist[own[k]], 1);
+      }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < num_shards; g += blockDim.x)
+      basepos[g] = hist[g] ? atomicAdd(&counts[g], hist[g]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = b0 + k * 256 + threadIdx.x;
+      if (own[k] >= 0) {
+        const int r = basepos[own[k]] + lr[k];
+        if (r < cap) {
+          const long long p = (long long)own[k] * cap + r;
+          send_ids[p] = ids[i];
+          if (send_occ) send_occ[p] = occ ? occ[i] : 1;
+          perm[i] = (int)p;
+        } else {
+          perm[i] = -1;  // does not fit: reported, the caller falls back to the exact path
+          atomicExch(overflow, 1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
@@ -547,6 +608,26 @@ int do_partition_ids(Workspace* ws, const int64_t* ids, int64_t n, const int32_t
   KV_LAUNCHED();
   partition_scatter_kernel<<<blocks_for(n, 256 * 8, dev), 256, 0, st>>>(
       k, n, d_n, num_shards, mode, offsets, cursors, reinterpret_cast<long long*>(sorted_ids), perm);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_route_ids(Workspace* ws, const int64_t* ids, const int32_t* occ, int64_t n,
+                 const int32_t* d_n, int num_shards, int mode, int cap, int64_t* send_ids,
+                 int32_t* send_occ, int32_t* perm, int32_t* counts, int32_t* overflow,
+                 cudaStream_t st) {
+  if (num_shards < 1 || num_shards > MAX_SHARDS)
+    return fail(1, "route_ids: num_shards must be in [1, 256]");
+  if (cap < 1) return fail(1, "route_ids: capacity must be positive");
+  const int dev = ws->device;
+  const long long total = (long long)num_shards * cap;
+  route_fill_kernel<<<blocks_for(total, 256, dev), 256, 0, st>>>(
+      reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards);
+  KV_LAUNCHED();
+  if (n <= 0) return 0;
+  route_scatter_kernel<<<blocks_for(n, 256 * 8, dev), 256, 0, st>>>(
+      reinterpret_cast<const long long*>(ids), occ, n, d_n, num_shards, mode, cap,
+      reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow);
   KV_LAUNCHED();
   return 0;
 }

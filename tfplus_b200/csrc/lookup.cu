@@ -83,7 +83,9 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
     long long pos = -1;
     uint32_t ctl = 0;
 
-    if (valid) {
+    if (valid && key == KEY_PAD) {
+      mode = M_ZERO;  // padding id of the shard exchange: zeros, no table access
+    } else if (valid) {
       Slot s;
       mode = M_ZERO;
       if (INSERT) {
@@ -322,7 +324,9 @@ gather_bulk_kernel(TableView t, const long long* __restrict__ ids,
     float* claim_row = nullptr;
     long long pos = -1;
     uint32_t ctl = 0;
-    if (valid) {
+    if (valid && key == KEY_PAD) {
+      mode = M_ZERO;  // padding id of the shard exchange: zeros, no table access
+    } else if (valid) {
       Slot s;
       mode = M_ZERO;
       if (INSERT) {
@@ -668,6 +672,61 @@ __global__ void permute_rows_kernel(const float* __restrict__ src, const int* __
   }
 }
 
+// out[i,:] = src[perm[idx[i]],:] (perm and/or idx may be null = identity): the requester side
+// of the shard exchange, un-permuting and expanding the deduplicated rows in one pass.
+__global__ void expand_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm,
+                                   const int* __restrict__ idx, long long n, int dim,
+                                   float* __restrict__ out) {
+  const int d4 = dim >> 2;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if ((dim & 3) == 0) {
+    for (; e < n * d4; e += stride) {
+      const long long r = e / d4;
+      const int c = (int)(e - r * d4);
+      long long p = idx ? idx[r] : r;
+      if (perm) p = perm[p];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p >= 0) v = __ldg(reinterpret_cast<const float4*>(src) + p * d4 + c);
+      reinterpret_cast<float4*>(out)[r * d4 + c] = v;
+    }
+  } else {
+    for (; e < n * dim; e += stride) {
+      const long long r = e / dim;
+      const int c = (int)(e - r * dim);
+      long long p = idx ? idx[r] : r;
+      if (perm) p = perm[p];
+      out[r * dim + c] = p >= 0 ? src[p * dim + c] : 0.f;
+    }
+  }
+}
+
+// out[perm[i],:] = src[i,:] for i < min(n, *d_n); rows with perm < 0 are dropped
+__global__ void scatter_rows_n_kernel(const float* __restrict__ src, const int* __restrict__ perm,
+                                      long long n, const int* __restrict__ d_n, int dim,
+                                      float* __restrict__ out) {
+  if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
+  const int d4 = dim >> 2;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if ((dim & 3) == 0) {
+    for (; e < n * d4; e += stride) {
+      const long long r = e / d4;
+      const int c = (int)(e - r * d4);
+      const long long p = perm[r];
+      if (p >= 0) reinterpret_cast<float4*>(out)[p * d4 + c] =
+          __ldg(reinterpret_cast<const float4*>(src) + r * d4 + c);
+    }
+  } else {
+    for (; e < n * dim; e += stride) {
+      const long long r = e / dim;
+      const int c = (int)(e - r * dim);
+      const long long p = perm[r];
+      if (p >= 0) out[p * dim + c] = src[r * dim + c];
+    }
+  }
+}
+
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
                   float* out, uint16_t today, cudaStream_t st, int tpr) {
@@ -808,6 +867,28 @@ int do_get_timestamp(Table* tb, const int64_t* ids, int64_t n, uint32_t* out, ui
   if (n <= 0) return 0;
   get_timestamp_kernel<<<blocks_for(n, 256, tb->device), 256, 0, st>>>(
       tb->view(), reinterpret_cast<const long long*>(ids), n, out, today);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_expand_rows(const float* src, const int32_t* perm, const int32_t* idx, int64_t n, int dim,
+                   float* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  const int64_t work = n * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
+  expand_rows_kernel<<<blocks_for(work, 256, dev, 16), 256, 0, st>>>(src, perm, idx, n, dim, out);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_scatter_rows_n(const float* src, const int32_t* perm, int64_t n, const int32_t* d_n,
+                      int dim, float* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  const int64_t work = n * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
+  scatter_rows_n_kernel<<<blocks_for(work, 256, dev, 16), 256, 0, st>>>(src, perm, n, d_n, dim, out);
   KV_LAUNCHED();
   return 0;
 }

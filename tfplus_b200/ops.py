@@ -629,6 +629,53 @@ def partition_ids(ids, num_shards, mode="hash", num_ids=None):
   return sorted_ids, perm, counts
 
 
+def route_ids(ids, occ, num_shards, capacity, mode="hash", num_ids=None, out=None):
+  """Fixed-capacity routing (kv_route_ids).  `out` = dict of preallocated send_ids
+  [num_shards*capacity] i64, send_occ (same, i32), perm [n] i32, counts [num_shards] i32,
+  overflow [1] i32 (all reused across calls so the exchange can be graph-captured)."""
+  n = ids.numel()
+  dev = ids.device
+  if out is None:
+    out = {"send_ids": torch.empty(num_shards * capacity, dtype=torch.int64, device=dev),
+           "send_occ": torch.empty(num_shards * capacity, dtype=torch.int32, device=dev),
+           "perm": torch.empty(n, dtype=torch.int32, device=dev),
+           "counts": torch.empty(num_shards, dtype=torch.int32, device=dev),
+           "overflow": torch.zeros(1, dtype=torch.int32, device=dev)}
+  ws = Workspace.get(dev)
+  with torch.cuda.device(dev):
+    check(_lib.load().kv_route_ids(ws.ptr, ids.data_ptr(), _ptr(occ), n, _ptr(num_ids),
+                                   num_shards, 1 if mode == "mod" else 0, capacity,
+                                   out["send_ids"].data_ptr(), out["send_occ"].data_ptr(),
+                                   out["perm"].data_ptr(), out["counts"].data_ptr(),
+                                   out["overflow"].data_ptr(), _stream(dev)))
+  return out
+
+
+def expand_rows(src, perm, idx, n, out):
+  """out[i] = src[perm[idx[i]]] (perm / idx may be None)."""
+  with torch.cuda.device(src.device):
+    check(_lib.load().kv_expand_rows(src.data_ptr(), _ptr(perm), _ptr(idx), n, src.shape[1],
+                                     out.data_ptr(), _stream(src.device)))
+  return out
+
+
+def scatter_rows_n(src, perm, n, num, out):
+  """out[perm[i]] = src[i] for i < min(n, num[0])."""
+  with torch.cuda.device(src.device):
+    check(_lib.load().kv_scatter_rows_n(src.data_ptr(), perm.data_ptr(), n, _ptr(num),
+                                        src.shape[1], out.data_ptr(), _stream(src.device)))
+  return out
+
+
+def unique_into(ids, uniq, idx, counts, num):
+  """kv_unique into caller-owned buffers (graph-capturable: nothing is allocated or read back)."""
+  ws = Workspace.get(ids.device)
+  with torch.cuda.device(ids.device):
+    check(_lib.load().kv_unique(ws.ptr, ids.data_ptr(), ids.numel(), uniq.data_ptr(),
+                                idx.data_ptr(), _ptr(counts), num.data_ptr(),
+                                _stream(ids.device)))
+
+
 def permute_rows(src, perm, out=None):
   """out[i] = src[perm[i]]."""
   src = src.contiguous()

@@ -16,6 +16,8 @@ is three exchanges over NVLink:
 The routing logic is backend-agnostic torch code: the product backend below is the CUDA one
 (tfplus_b200.ops -> C ABI); tests drive the same logic with world_size-2 gloo on CPU.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -153,6 +155,76 @@ class ShardedKvVariable:
     return self.router.send_grads(route or self.last_route, grad)
 
 
+class PaddedShardedStep:
+  """The sync-free sharded step: every buffer has a data-independent shape, so the whole
+  forward + backward (kernels and the NCCL all-to-alls between them) is captured in one CUDA
+  graph and replayed; no host round trip anywhere.
+
+  Exchange layout: each rank sends each peer a fixed `cap` ids (padded with the pad id, which
+  lookups answer with zeros and applies skip).  `cap` defaults to batch / (2 * world) + 1024:
+  ~1.5x the expected unique ids per peer for the Zipf(1.1) batch; if a row overflows, the
+  overflow flag is raised on the device and the caller must rerun the step on the exact
+  (variable-size) path of ShardedKvVariable.
+  """
+
+  def __init__(self, var, slot, dim, batch, world, rank, dev, hpt, betas, cap=None, group=None,
+               mode="hash"):
+    t = torch
+    self.var, self.slot, self.dim, self.batch = var, slot, dim, batch
+    self.world, self.rank, self.dev, self.group, self.mode = world, rank, dev, group, mode
+    self.hpt, self.betas = hpt, betas
+    self.cap = cap or (batch // (2 * world) + 1024) // 2 * 2
+    B, G, C, D = batch, world, self.cap, dim
+    i64 = dict(dtype=t.int64, device=dev)
+    i32 = dict(dtype=t.int32, device=dev)
+    f32 = dict(dtype=t.float32, device=dev)
+    self.uniq, self.idx = t.empty(B, **i64), t.empty(B, **i32)
+    self.cnt, self.num = t.empty(B, **i32), t.zeros(1, **i32)
+    self.route = {"send_ids": t.empty(G * C, **i64), "send_occ": t.empty(G * C, **i32),
+                  "perm": t.empty(B, **i32), "counts": t.empty(G, **i32),
+                  "overflow": t.zeros(1, **i32)}
+    self.recv_ids, self.recv_occ = t.empty(G * C, **i64), t.empty(G * C, **i32)
+    self.rows_owner, self.rows_recv = t.empty(G * C, D, **f32), t.empty(G * C, D, **f32)
+    self.out = t.empty(B, D, **f32)
+    self.gsum = t.empty(B, D, **f32)
+    self.g_send, self.g_recv = t.zeros(G * C, D, **f32), t.empty(G * C, D, **f32)
+    self.o_uniq, self.o_idx = t.empty(G * C, **i64), t.empty(G * C, **i32)
+    self.o_num = t.zeros(1, **i32)
+    self.o_gsum = t.empty(G * C, D, **f32)
+    self.wire_bytes = (G - 1) * C * (8 + 4 + 2 * 4 * D)  # per step, sent by this rank
+
+  def _a2a(self, out, inp):
+    if self.world == 1:
+      out.copy_(inp)
+    else:
+      dist.all_to_all_single(out, inp, group=self.group)
+
+  def run(self, ids, grad):
+    B, G, C, D = self.batch, self.world, self.cap, self.dim
+    # ---- forward: dedup, route, exchange, owner lookup, rows back ----
+    ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
+    ops.route_ids(self.uniq, self.cnt, G, C, self.mode, num_ids=self.num, out=self.route)
+    self._a2a(self.recv_ids, self.route["send_ids"])
+    self._a2a(self.recv_occ, self.route["send_occ"])
+    ops.kv_variable_gather_or_insert_with_counts(self.var, self.recv_ids, self.recv_occ,
+                                                 out=self.rows_owner)
+    self._a2a(self.rows_recv, self.rows_owner)
+    ops.expand_rows(self.rows_recv, self.route["perm"], self.idx, B, self.out)
+    # ---- backward: local sum, route gradients, owner merge, fused apply ----
+    ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
+    ops.scatter_rows_n(self.gsum, self.route["perm"], B, self.num, self.g_send)
+    self._a2a(self.g_recv, self.g_send)
+    ops.unique_into(self.recv_ids, self.o_uniq, self.o_idx, None, self.o_num)
+    ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum)
+    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
+                                                   self.hpt, num_indices=self.o_num)
+    self.hpt[1:3].mul_(self.betas)
+    return self.out
+
+  def overflowed(self):
+    return bool(self.route["overflow"].item())
+
+
 # ---------------------------------------------------------------------------
 # bench driver (bench.py --gpus N)
 # ---------------------------------------------------------------------------
@@ -194,47 +266,70 @@ class ShardedStepper:
         ops.kv_variable_gather_or_insert_v2(self.tbl.slots[0], mine)
     t.cuda.synchronize()
 
-  def step_eager(self, ids, grad):
+  def step_exact(self, ids, grad):
+    """The variable-size path (host reads the per-shard counts): reference behaviour for the
+    padded path and its fallback on overflow."""
     rows = self.tbl.lookup(ids)
     owner_ids, owner_grads = self.tbl.owner_gradients(grad)
     if owner_ids.numel():
       ops.kv_variable_group_sparse_apply_adam_v4_dev(self.tbl.var, self.tbl.slots[0], owner_grads,
                                                      owner_ids, self.hpt)
     self.hpt[1:3].mul_(self.betas)
-    self.steps_done += 1
     return rows
+
+  def step_eager(self, ids, grad):
+    self.steps_done += 1
+    return self.padded.run(ids, grad)
 
   def prepare(self, ids_d, grads_d):
     from . import _lib
+    t = self.torch
     self.ids_d, self.grads_d = ids_d, grads_d
+    self.padded = PaddedShardedStep(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
+                                    self.world, self.rank, self.dev, self.hpt, self.betas)
     l0 = _lib.launch_count()
     for i in range(2):
       self.step_eager(ids_d[i], grads_d[i])
     self.launches_per_step = (_lib.launch_count() - l0) // 2
-    self.torch.cuda.synchronize()
+    t.cuda.synchronize()
+    if self.padded.overflowed():
+      raise RuntimeError("padded shard exchange overflowed: raise cap")
+    ops.kv_variable_reserve(self.tbl.var, 2 * self.padded.cap * self.world)
+    ops.kv_variable_reserve(self.tbl.slots[0], 2 * self.padded.cap * self.world)
+    self.graphs = []
+    if os.environ.get("KVHBM_SHARDED_GRAPH", "1") != "0":
+      side = t.cuda.Stream(device=self.dev)
+      side.wait_stream(t.cuda.current_stream(self.dev))
+      with t.cuda.stream(side):
+        for i in range(len(ids_d)):
+          g = t.cuda.CUDAGraph()
+          with t.cuda.graph(g, stream=side):
+            self.padded.run(ids_d[i], grads_d[i])
+          self.graphs.append(g)
+      t.cuda.current_stream(self.dev).wait_stream(side)
+      t.cuda.synchronize()
 
   def step(self, i):
     k = i % len(self.ids_d)
-    return self.step_eager(self.ids_d[k], self.grads_d[k])
+    self.steps_done += 1
+    if self.graphs:
+      self.graphs[k].replay()
+      return self.padded.out
+    return self.padded.run(self.ids_d[k], self.grads_d[k])
+
+  def release(self):
+    self.graphs = []
 
   def stage_times(self, steps):
     t = self.torch
-    acc = [0.0, 0.0]
+    a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    t.cuda.synchronize()
+    a.record()
     for i in range(steps):
-      k = i % len(self.ids_d)
-      e = [t.cuda.Event(enable_timing=True) for _ in range(3)]
-      e[0].record()
-      self.tbl.lookup(self.ids_d[k])
-      e[1].record()
-      owner_ids, owner_grads = self.tbl.owner_gradients(self.grads_d[k])
-      if owner_ids.numel():
-        ops.kv_variable_group_sparse_apply_adam_v4_dev(self.tbl.var, self.tbl.slots[0],
-                                                       owner_grads, owner_ids, self.hpt)
-      e[2].record()
-      t.cuda.synchronize()
-      acc[0] += e[0].elapsed_time(e[1])
-      acc[1] += e[1].elapsed_time(e[2])
-    return {self.STAGES[0]: acc[0] / steps, self.STAGES[1]: acc[1] / steps}
+      self.step(i)
+    b.record()
+    t.cuda.synchronize()
+    return {"sharded step": a.elapsed_time(b) / steps}
 
   def prepare_host(self, ids_h, grads_h, rows_h):
     t = self.torch
@@ -249,5 +344,6 @@ class ShardedStepper:
     k = i % len(self.ids_h)
     self.h_ids.copy_(self.ids_h[k], non_blocking=True)
     self.h_grad.copy_(self.grads_h[k], non_blocking=True)
-    rows = self.step_eager(self.h_ids, self.h_grad)
+    rows = self.padded.run(self.h_ids, self.h_grad)
+    self.steps_done += 1
     self.rows_h.copy_(rows, non_blocking=True)
