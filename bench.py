@@ -190,7 +190,7 @@ def main_reference(args):
       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
-  print(json.dumps(line))
+  emit_json(line)
   return 0
 
 
@@ -351,9 +351,9 @@ def main_ours(args):
       line["nvlink"] = {"bytes_sent_per_gpu_per_step": sent,
                         "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
                         "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
-                        "exchanges_per_step": 4, "capacity_per_peer": stepper.padded.cap,
+                        "exchanges_per_step": 3, "capacity_per_peer": stepper.padded.cap,
                         "overflowed": stepper.padded.overflowed(),
-                        "note": "fixed-capacity all_to_all of ids, occurrence counts, rows, "
+                        "note": "fixed-capacity all_to_all of {id, occurrence count} pairs, rows, "
                                 "gradients, captured with the kernels in one CUDA graph"}
       line["stage_ms"] = stage_ms
     if world == 1 and not args.no_cpu:
@@ -364,7 +364,7 @@ def main_ours(args):
           "value": v, "unit": UNIT, "cores": cores, "kind": "port",
           "sample": "same workload (%d-key table), %d timed steps of B=%d after 2 warm-up, "
                     "oracle port of the reference algorithm, %d threads" % (keys, cs, B, cores)}
-    print(json.dumps(line))
+    emit_json(line)
   if world > 1:
     stepper.release()      # captured NCCL work must be gone before the process group
     torch.cuda.synchronize()
@@ -577,7 +577,35 @@ class LocalStepper:
     main.wait_stream(self.s_d2h)
 
 
+class _QuietStdout:
+  """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on
+  stdout.  Everything written to fd 1 while this is active goes to stderr instead; emit() writes
+  to the real stdout."""
+
+  def __init__(self):
+    sys.stdout.flush()
+    self._real = os.dup(1)
+    os.dup2(2, 1)
+
+  def emit(self, text):
+    sys.stdout.flush()
+    os.write(self._real, (text + "\n").encode())
+
+
+_OUT = None
+
+
+def emit_json(line):
+  text = json.dumps(line)
+  if _OUT is not None:
+    _OUT.emit(text)
+  else:
+    print(text)
+
+
 def main():
+  global _OUT
+  _OUT = _QuietStdout()
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=200)

@@ -250,6 +250,15 @@ int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, i
                  const int32_t* d_n, int num_shards, int mode, int capacity,
                  int64_t* d_send_ids, int32_t* d_send_occ, int32_t* d_perm,
                  int32_t* d_counts, int32_t* d_overflow, kv_stream stream);
+/* Same, but ids and occurrence counts travel together as interleaved
+ * {int64 id, int64 count} pairs in d_send_pairs[num_shards][capacity][2], so
+ * one exchange carries both; kv_unzip_pairs splits what was received. */
+int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                      const int32_t* d_n, int num_shards, int mode, int capacity,
+                      int64_t* d_send_pairs, int32_t* d_perm, int32_t* d_counts,
+                      int32_t* d_overflow, kv_stream stream);
+int kv_unzip_pairs(const int64_t* d_pairs, int64_t n, int64_t* d_ids, int32_t* d_occ,
+                   kv_stream stream);
 /* out[i, :] = src[perm[idx[i]], :]; perm and/or idx may be NULL (identity); a
  * negative perm entry yields zeros. */
 int kv_expand_rows(const float* d_src, const int32_t* d_perm, const int32_t* d_idx, int64_t n,

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""torchrun -n 2 scripts/profile_sharded.py : kernel-time table of the sharded step (rank 0)."""
+import os, sys
+import torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from tfplus_b200 import ops, sharded
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+ops.set_today(bench.TODAY)
+keys = int(os.environ.get("KEYS", "2000000"))
+st = sharded.ShardedStepper(keys, bench.DIM, bench.BATCH, bench.HP, dev, rank, world)
+st.populate()
+ids_np, g_np = bench.make_batches(4, keys * world, bench.BATCH, bench.DIM, seed_ids=2024 + rank, seed_grad=7 + rank)
+ids = [torch.from_numpy(x).to(dev) for x in ids_np]
+gr = [torch.from_numpy(x).to(dev) for x in g_np]
+os.environ["KVHBM_SHARDED_GRAPH"] = "0"
+st.prepare(ids, gr)
+for i in range(5): st.step(i)
+torch.cuda.synchronize(); dist.barrier()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+  for i in range(10): st.step(i)
+  torch.cuda.synchronize()
+if rank == 0:
+  rows = []
+  for e in prof.key_averages():
+    t = getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0)
+    if t: rows.append((t / 10.0, e.count / 10.0, e.key[:70]))
+  rows.sort(reverse=True)
+  tot = sum(r[0] for r in rows)
+  print("kernel time per step: %.1f us" % tot)
+  for r in rows[:25]: print("%8.1f us  x%.1f  %s" % r)
+dist.barrier(); dist.destroy_process_group()

@@ -60,6 +60,8 @@ SIGNATURES = {
     "kv_delete_with_timestamp": [vp, i32, u16, vp, i64, vp, C.POINTER(i64)],
     "kv_partition_ids": [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp],
     "kv_route_ids": [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
+    "kv_route_id_pairs": [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp],
+    "kv_unzip_pairs": [vp, i64, vp, vp, vp],
     "kv_expand_rows": [vp, vp, vp, i64, i32, vp, vp],
     "kv_scatter_rows_n": [vp, vp, i64, vp, i32, vp, vp],
     "kv_permute_rows": [vp, vp, i64, i32, vp, vp],

@@ -43,7 +43,8 @@ int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, i
                      int32_t*, int32_t*, cudaStream_t);
 
 int do_route_ids(Workspace*, const int64_t*, const int32_t*, int64_t, const int32_t*, int, int, int,
-                 int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+                 int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, int pairs, cudaStream_t);
+int do_unzip_pairs(const int64_t*, int64_t, int64_t*, int32_t*, cudaStream_t);
 int do_expand_rows(const float*, const int32_t*, const int32_t*, int64_t, int, float*, cudaStream_t);
 int do_scatter_rows_n(const float*, const int32_t*, int64_t, const int32_t*, int, float*,
                       cudaStream_t);
@@ -405,7 +406,20 @@ int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, i
   KV_NEED(ws && d_send_ids && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
           "route_ids: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_ids,
-                      d_send_occ, d_perm, d_counts, d_overflow, S(stream));
+                      d_send_occ, d_perm, d_counts, d_overflow, /*pairs=*/0, S(stream));
+}
+int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                      const int32_t* d_n, int num_shards, int mode, int capacity,
+                      int64_t* d_send_pairs, int32_t* d_perm, int32_t* d_counts,
+                      int32_t* d_overflow, kv_stream stream) {
+  KV_NEED(ws && d_send_pairs && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
+          "route_id_pairs: bad arguments");
+  return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_pairs,
+                      nullptr, d_perm, d_counts, d_overflow, /*pairs=*/1, S(stream));
+}
+int kv_unzip_pairs(const int64_t* d_pairs, int64_t n, int64_t* d_ids, int32_t* d_occ,
+                   kv_stream stream) {
+  return do_unzip_pairs(d_pairs, n, d_ids, d_occ, S(stream));
 }
 int kv_expand_rows(const float* d_src, const int32_t* d_perm, const int32_t* d_idx, int64_t n,
                    int dim, float* d_out, kv_stream stream) {

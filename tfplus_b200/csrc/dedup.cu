@@ -423,22 +423,39 @@ partition_scatter_kernel(const long long* __restrict__ ids, long long n, const i
 // send_ids / send_occ are [num_shards][cap]: the ids owned by shard g go to [g][0 .. count_g),
 // the rest of each row is padding (KEY_PAD / 0).  Shapes do not depend on the data, so the
 // exchange that follows needs no host synchronisation and can be captured in a CUDA graph.
+// pairs != 0: send_ids holds interleaved {id, occurrence count} int64 pairs (one exchange
+// carries both); otherwise ids and counts go to two separate arrays.
 __global__ void route_fill_kernel(long long* send_ids, int* send_occ, long long total, int* counts,
-                                  int num_shards) {
+                                  int num_shards, int pairs) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < total; j += stride) {
-    send_ids[j] = KEY_PAD;
-    if (send_occ) send_occ[j] = 0;
+    if (pairs) { send_ids[2 * j] = KEY_PAD; send_ids[2 * j + 1] = 0; }
+    else {
+      send_ids[j] = KEY_PAD;
+      if (send_occ) send_occ[j] = 0;
+    }
   }
   if (i < num_shards) counts[i] = 0;
+}
+
+__global__ void unzip_pairs_kernel(const long long* __restrict__ pairs, long long n,
+                                   long long* __restrict__ ids, int* __restrict__ occ) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(pairs) + i);
+    ids[i] = v.x;
+    occ[i] = (int)v.y;
+  }
 }
 
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ occ, long long n,
                      const int* d_n, int num_shards, int mode, int cap,
                      long long* __restrict__ send_ids, int* __restrict__ send_occ,
-                     int* __restrict__ perm, int* __restrict__ counts, int* __restrict__ overflow) {
+                     int* __restrict__ perm, int* __restrict__ counts, int* __restrict__ overflow,
+                     int pairs) {
   __shared__ int hist[MAX_SHARDS];
   __shared__ int basepos[MAX_SHARDS];
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
@@ -467,8 +484,12 @@ route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ 
         const int r = basepos[own[k]] + lr[k];
         if (r < cap) {
           const long long p = (long long)own[k] * cap + r;
-          send_ids[p] = ids[i];
-          if (send_occ) send_occ[p] = occ ? occ[i] : 1;
+          if (pairs) {
+            reinterpret_cast<longlong2*>(send_ids)[p] = make_longlong2(ids[i], occ ? occ[i] : 1);
+          } else {
+            send_ids[p] = ids[i];
+            if (send_occ) send_occ[p] = occ ? occ[i] : 1;
+          }
           perm[i] = (int)p;
         } else {
           perm[i] = -1;  // does not fit: reported, the caller falls back to the exact path
@@ -614,7 +635,7 @@ int do_partition_ids(Workspace* ws, const int64_t* ids, int64_t n, const int32_t
 
 int do_route_ids(Workspace* ws, const int64_t* ids, const int32_t* occ, int64_t n,
                  const int32_t* d_n, int num_shards, int mode, int cap, int64_t* send_ids,
-                 int32_t* send_occ, int32_t* perm, int32_t* counts, int32_t* overflow,
+                 int32_t* send_occ, int32_t* perm, int32_t* counts, int32_t* overflow, int pairs,
                  cudaStream_t st) {
   if (num_shards < 1 || num_shards > MAX_SHARDS)
     return fail(1, "route_ids: num_shards must be in [1, 256]");
@@ -622,12 +643,22 @@ int do_route_ids(Workspace* ws, const int64_t* ids, const int32_t* occ, int64_t 
   const int dev = ws->device;
   const long long total = (long long)num_shards * cap;
   route_fill_kernel<<<blocks_for(total, 256, dev), 256, 0, st>>>(
-      reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards);
+      reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards, pairs);
   KV_LAUNCHED();
   if (n <= 0) return 0;
   route_scatter_kernel<<<blocks_for(n, 256 * 8, dev), 256, 0, st>>>(
       reinterpret_cast<const long long*>(ids), occ, n, d_n, num_shards, mode, cap,
-      reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow);
+      reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow, pairs);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_unzip_pairs(const int64_t* pairs, int64_t n, int64_t* ids, int32_t* occ, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  unzip_pairs_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(
+      reinterpret_cast<const long long*>(pairs), n, reinterpret_cast<long long*>(ids), occ);
   KV_LAUNCHED();
   return 0;
 }

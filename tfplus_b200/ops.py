@@ -651,6 +651,25 @@ def route_ids(ids, occ, num_shards, capacity, mode="hash", num_ids=None, out=Non
   return out
 
 
+def route_id_pairs(ids, occ, num_shards, capacity, mode, num_ids, out):
+  """kv_route_id_pairs: out = dict(send_pairs [num_shards*capacity*2] i64, perm, counts,
+  overflow)."""
+  ws = Workspace.get(ids.device)
+  with torch.cuda.device(ids.device):
+    check(_lib.load().kv_route_id_pairs(ws.ptr, ids.data_ptr(), _ptr(occ), ids.numel(),
+                                        _ptr(num_ids), num_shards, 1 if mode == "mod" else 0,
+                                        capacity, out["send_pairs"].data_ptr(),
+                                        out["perm"].data_ptr(), out["counts"].data_ptr(),
+                                        out["overflow"].data_ptr(), _stream(ids.device)))
+  return out
+
+
+def unzip_pairs(pairs, ids, occ):
+  with torch.cuda.device(pairs.device):
+    check(_lib.load().kv_unzip_pairs(pairs.data_ptr(), ids.numel(), ids.data_ptr(),
+                                     occ.data_ptr(), _stream(pairs.device)))
+
+
 def expand_rows(src, perm, idx, n, out):
   """out[i] = src[perm[idx[i]]] (perm / idx may be None)."""
   with torch.cuda.device(src.device):

@@ -180,9 +180,11 @@ class PaddedShardedStep:
     f32 = dict(dtype=t.float32, device=dev)
     self.uniq, self.idx = t.empty(B, **i64), t.empty(B, **i32)
     self.cnt, self.num = t.empty(B, **i32), t.zeros(1, **i32)
-    self.route = {"send_ids": t.empty(G * C, **i64), "send_occ": t.empty(G * C, **i32),
-                  "perm": t.empty(B, **i32), "counts": t.empty(G, **i32),
-                  "overflow": t.zeros(1, **i32)}
+    self.pairs = os.environ.get("KVHBM_SHARDED_PAIRS", "1") != "0"
+    self.route = {"send_pairs": t.empty(G * C * 2, **i64), "perm": t.empty(B, **i32),
+                  "counts": t.empty(G, **i32), "overflow": t.zeros(1, **i32),
+                  "send_ids": t.empty(G * C, **i64), "send_occ": t.empty(G * C, **i32)}
+    self.recv_pairs = t.empty(G * C * 2, **i64)
     self.recv_ids, self.recv_occ = t.empty(G * C, **i64), t.empty(G * C, **i32)
     self.rows_owner, self.rows_recv = t.empty(G * C, D, **f32), t.empty(G * C, D, **f32)
     self.out = t.empty(B, D, **f32)
@@ -191,7 +193,8 @@ class PaddedShardedStep:
     self.o_uniq, self.o_idx = t.empty(G * C, **i64), t.empty(G * C, **i32)
     self.o_num = t.zeros(1, **i32)
     self.o_gsum = t.empty(G * C, D, **f32)
-    self.wire_bytes = (G - 1) * C * (8 + 4 + 2 * 4 * D)  # per step, sent by this rank
+    self.wire_bytes = (G - 1) * C * (16 + 2 * 4 * D)  # per step, sent by this rank
+    self.side = t.cuda.Stream(device=dev)
 
   def _a2a(self, out, inp):
     if self.world == 1:
@@ -200,22 +203,44 @@ class PaddedShardedStep:
       dist.all_to_all_single(out, inp, group=self.group)
 
   def run(self, ids, grad):
+    """All NCCL calls stay on the calling stream in a fixed order; work that only depends on
+    the ids (local gradient sum, the owner-side dedup) runs on a side stream underneath the
+    exchanges and is joined where its result is needed."""
     B, G, C, D = self.batch, self.world, self.cap, self.dim
+    t = torch
+    main = t.cuda.current_stream(self.dev)
+    side = self.side
     # ---- forward: dedup, route, exchange, owner lookup, rows back ----
     ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
-    ops.route_ids(self.uniq, self.cnt, G, C, self.mode, num_ids=self.num, out=self.route)
-    self._a2a(self.recv_ids, self.route["send_ids"])
-    self._a2a(self.recv_occ, self.route["send_occ"])
+    if self.pairs:
+      ops.route_id_pairs(self.uniq, self.cnt, G, C, self.mode, self.num, self.route)
+    else:
+      ops.route_ids(self.uniq, self.cnt, G, C, self.mode, num_ids=self.num, out=self.route)
+    side.wait_stream(main)
+    with t.cuda.stream(side):      # backward, local half: sum duplicate gradients, lay them out
+      ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
+      ops.scatter_rows_n(self.gsum, self.route["perm"], B, self.num, self.g_send)
+    if self.pairs:
+      self._a2a(self.recv_pairs, self.route["send_pairs"])   # ids + occurrence counts together
+      ops.unzip_pairs(self.recv_pairs, self.recv_ids, self.recv_occ)
+    else:
+      self._a2a(self.recv_ids, self.route["send_ids"])
+      self._a2a(self.recv_occ, self.route["send_occ"])
+    ev_ids = t.cuda.Event()
+    ev_ids.record(main)
+    with t.cuda.stream(side):      # backward, owner half: dedup what the peers sent
+      side.wait_event(ev_ids)
+      ops.unique_into(self.recv_ids, self.o_uniq, self.o_idx, None, self.o_num)
+      ops.zero_rows(self.o_gsum)
     ops.kv_variable_gather_or_insert_with_counts(self.var, self.recv_ids, self.recv_occ,
                                                  out=self.rows_owner)
     self._a2a(self.rows_recv, self.rows_owner)
     ops.expand_rows(self.rows_recv, self.route["perm"], self.idx, B, self.out)
-    # ---- backward: local sum, route gradients, owner merge, fused apply ----
-    ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
-    ops.scatter_rows_n(self.gsum, self.route["perm"], B, self.num, self.g_send)
+    # ---- backward: route gradients, owner merge, fused apply ----
+    main.wait_stream(side)
     self._a2a(self.g_recv, self.g_send)
-    ops.unique_into(self.recv_ids, self.o_uniq, self.o_idx, None, self.o_num)
-    ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum)
+    ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum,
+                             accumulate=True)
     ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
                                                    self.hpt, num_indices=self.o_num)
     self.hpt[1:3].mul_(self.betas)
