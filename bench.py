@@ -83,10 +83,14 @@ def algorithmic_bytes(b, u, d):
 class ClockSampler:
   """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-  def __init__(self, index):
+  def __init__(self, index, enabled=True, period_s=0.002):
     self.samples, self.reasons, self.max_mhz = [], set(), None
     self._stop = threading.Event()
     self._t = None
+    self.period_s = period_s
+    self.nv = None
+    if not enabled:
+      return
     try:
       import pynvml
       pynvml.nvmlInit()
@@ -119,7 +123,7 @@ class ClockSampler:
           self._once()
         except Exception:
           return
-        time.sleep(0.002)
+        time.sleep(self.period_s)
     self._t = threading.Thread(target=run, daemon=True)
     self._t.start()
 
@@ -262,7 +266,11 @@ def main_ours(args):
   for i in range(W):
     stepper.step(i)
   barrier()
-  clocks = ClockSampler(local_rank)
+  # NVML queries take driver locks: with every rank polling, the ranks stall each other through
+  # the exchange (measured 2x on the 8-GPU step), so only rank 0 samples, and less often
+  all_ranks = os.environ.get("KVHBM_BENCH_CLOCK_RANKS", "0") == "all"
+  clocks = ClockSampler(local_rank, enabled=(rank == 0 or all_ranks),
+                        period_s=0.002 if world == 1 or all_ranks else 0.005)
   clocks.start()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
@@ -348,13 +356,20 @@ def main_ours(args):
     }
     if world > 1:
       sent = stepper.padded.wire_bytes
-      line["nvlink"] = {"bytes_sent_per_gpu_per_step": sent,
+      peer = hasattr(stepper.padded, "barrier_timeouts")
+      if peer and stepper.padded.barrier_timeouts():
+        raise SystemExit("peer barrier timed out %d times: the step is invalid"
+                         % stepper.padded.barrier_timeouts())
+      line["nvlink"] = {"exchange": "peer-memory stores fused into the producing kernels + "
+                                    "3 barrier kernels" if peer else "NCCL all_to_all_single x3",
+                        "bytes_sent_per_gpu_per_step": sent,
                         "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
                         "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
                         "exchanges_per_step": 3, "capacity_per_peer": stepper.padded.cap,
                         "overflowed": stepper.padded.overflowed(),
-                        "note": "fixed-capacity all_to_all of {id, occurrence count} pairs, rows, "
-                                "gradients, captured with the kernels in one CUDA graph"}
+                        "note": "fixed-capacity exchange of {id, occurrence count} pairs, rows, "
+                                "gradients (bytes = capacity upper bound), captured with the "
+                                "kernels in one CUDA graph"}
       line["stage_ms"] = stage_ms
     if world == 1 and not args.no_cpu:
       cores = os.cpu_count() or 1

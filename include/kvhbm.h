@@ -273,6 +273,35 @@ int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int di
 int kv_scatter_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim,
                     float* d_out, kv_stream stream);
 
+/* ---- Peer-memory (NVLink / NVSwitch) variants: compute fused with its exchange ----
+ * The three exchanges of the sharded step as stores of the producing kernel into
+ * buffers that live on the PEER GPUs (memory the host maps into this process:
+ * symmetric memory / cudaIpc; the library only sees device pointers).  A
+ * `d_seg` argument is a DEVICE array of num_shards device pointers; segment g
+ * holds `capacity` entries and normally points at peer g's buffer + rank * capacity.
+ * Replaces the PS<->worker send/recv around the ops of SURVEY.md §8e.          */
+/* kv_route_id_pairs whose {id, count} pairs go straight to d_seg_pairs[g][0..capacity). */
+int kv_route_id_pairs_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ,
+                           int64_t n, const int32_t* d_n, int num_shards, int mode, int capacity,
+                           int64_t* const* d_seg_pairs, int32_t* d_perm, int32_t* d_counts,
+                           int32_t* d_overflow, kv_stream stream);
+/* kv_gather_or_insert whose row r is written to d_seg_rows[r / capacity] + (r % capacity) * dim;
+ * rows of padding ids are not written at all. */
+int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
+                             int64_t n, float* const* d_seg_rows, int64_t capacity,
+                             uint16_t today, kv_stream stream);
+/* kv_scatter_rows_n whose destination row p is d_seg_rows[p / capacity] + (p % capacity) * dim. */
+int kv_scatter_rows_n_peer(const float* d_src, const int32_t* d_perm, int64_t n,
+                           const int32_t* d_n, int dim, float* const* d_seg_rows,
+                           int64_t capacity, kv_stream stream);
+/* Barrier among the `world` GPUs, as one kernel on `stream` (CUDA-graph capturable):
+ * everything the peers stored before their call is visible after it.  d_peer_flags is a
+ * device array of world pointers to every rank's flag array (uint32[world], zero-initialised,
+ * peer-mapped); d_my_flags is this rank's own; d_state is local uint32[2], zero-initialised:
+ * [0] counts completed barriers, [1] counts waits given up after timeout_ms. */
+int kv_peer_barrier(uint32_t* const* d_peer_flags, uint32_t* d_my_flags, uint32_t* d_state,
+                    int rank, int world, int64_t timeout_ms, kv_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

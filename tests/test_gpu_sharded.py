@@ -178,12 +178,13 @@ def test_pad_ids_are_ignored_and_row_helpers():
   np.testing.assert_array_equal(dst.cpu().numpy(), want)
 
 
-def _padded_worker(rank, world, port, q, use_graph):
+def _padded_worker(rank, world, port, q, use_graph, exchange="nccl"):
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
   torch.cuda.set_device(rank)
   dev = torch.device("cuda", rank)
   dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-  from tfplus_b200.sharded import PaddedShardedStep
+  from tfplus_b200.sharded import PaddedShardedStep, PeerShardedStep
+  Step = PeerShardedStep if exchange == "peer" else PaddedShardedStep
   ops.set_today(TODAY)
   var = ops.kv_variable(value_shape=[D], enter_threshold=0, device=dev, seed=5, capacity_hint=4096)
   slot = ops.kv_variable(value_shape=[3 * D], device=dev, seed=5, capacity_hint=4096)
@@ -191,7 +192,7 @@ def _padded_worker(rank, world, port, q, use_graph):
   ops.init_kv_variable_v2(slot, torch.zeros(16, 3 * D, device=dev))
   hp = torch.tensor([0.05, 0.9, 0.999, 0.9, 0.999, 1e-8, 1e-5, 1e-5, 1e-5], device=dev)
   betas = torch.tensor([0.9, 0.999], device=dev)
-  step = PaddedShardedStep(var, slot, D, 400, world, rank, dev, hp, betas, cap=256)
+  step = Step(var, slot, D, 400, world, rank, dev, hp, betas, cap=256)
   data = [batches(world, s) for s in range(3)]
   ids = [torch.from_numpy(d[0][rank]).to(dev) for d in data]
   grads = [torch.from_numpy(d[1][rank]).to(dev) for d in data]
@@ -220,6 +221,8 @@ def _padded_worker(rank, world, port, q, use_graph):
     for s in range(3):
       looked.append(step.run(ids[s], grads[s]).cpu().numpy().copy())
   assert not step.overflowed()
+  if exchange == "peer":
+    assert step.barrier_timeouts() == 0
   k, v, _, _, fk, fv = ops.kv_variable_export(var, first_n=6, enable_cutoff=True,
                                               cutoff_value=1e-20, freq_dtype=torch.int32)
   q.put((rank, looked, k.cpu().numpy(), v.cpu().numpy(), fk.cpu().numpy(),
@@ -229,13 +232,15 @@ def _padded_worker(rank, world, port, q, use_graph):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_padded_sharded_step_equals_one_table(use_graph):
+def test_padded_sharded_step_equals_one_table(use_graph, exchange):
   world = 2
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
   port = _free_port()
-  procs = [ctx.Process(target=_padded_worker, args=(r, world, port, q, use_graph)) for r in range(world)]
+  procs = [ctx.Process(target=_padded_worker, args=(r, world, port, q, use_graph, exchange))
+           for r in range(world)]
   for p in procs:
     p.start()
   results = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])

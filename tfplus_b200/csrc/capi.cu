@@ -43,11 +43,15 @@ int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, i
                      int32_t*, int32_t*, cudaStream_t);
 
 int do_route_ids(Workspace*, const int64_t*, const int32_t*, int64_t, const int32_t*, int, int, int,
-                 int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, int pairs, cudaStream_t);
+                 int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, int pairs, int64_t* const*,
+                 cudaStream_t);
+int do_gather_segments(Table*, const int64_t*, const int32_t*, int64_t, float* const*, int64_t,
+                       uint16_t, cudaStream_t);
+int do_peer_barrier(uint32_t* const*, uint32_t*, uint32_t*, int, int, int64_t, cudaStream_t);
 int do_unzip_pairs(const int64_t*, int64_t, int64_t*, int32_t*, cudaStream_t);
 int do_expand_rows(const float*, const int32_t*, const int32_t*, int64_t, int, float*, cudaStream_t);
 int do_scatter_rows_n(const float*, const int32_t*, int64_t, const int32_t*, int, float*,
-                      cudaStream_t);
+                      float* const*, int64_t, cudaStream_t);
 int do_stats(Table*, cudaStream_t, int64_t*, int64_t*, int64_t*);
 int do_export_count(Table*, int, int, float, cudaStream_t, int64_t*, int64_t*, int64_t*);
 int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cudaStream_t);
@@ -406,7 +410,7 @@ int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, i
   KV_NEED(ws && d_send_ids && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
           "route_ids: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_ids,
-                      d_send_occ, d_perm, d_counts, d_overflow, /*pairs=*/0, S(stream));
+                      d_send_occ, d_perm, d_counts, d_overflow, /*pairs=*/0, nullptr, S(stream));
 }
 int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
                       const int32_t* d_n, int num_shards, int mode, int capacity,
@@ -415,7 +419,32 @@ int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_o
   KV_NEED(ws && d_send_pairs && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
           "route_id_pairs: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_pairs,
-                      nullptr, d_perm, d_counts, d_overflow, /*pairs=*/1, S(stream));
+                      nullptr, d_perm, d_counts, d_overflow, /*pairs=*/1, nullptr, S(stream));
+}
+int kv_route_id_pairs_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ,
+                           int64_t n, const int32_t* d_n, int num_shards, int mode, int capacity,
+                           int64_t* const* d_seg_pairs, int32_t* d_perm, int32_t* d_counts,
+                           int32_t* d_overflow, kv_stream stream) {
+  KV_NEED(ws && d_seg_pairs && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
+          "route_id_pairs_peer: bad arguments");
+  return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, nullptr, nullptr,
+                      d_perm, d_counts, d_overflow, /*pairs=*/1, d_seg_pairs, S(stream));
+}
+int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
+                             int64_t n, float* const* d_seg_rows, int64_t capacity,
+                             uint16_t today, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_seg_rows)), "gather_or_insert_peer: bad arguments");
+  return do_gather_segments(&t->t, d_ids, d_counts, n, d_seg_rows, capacity, today, S(stream));
+}
+int kv_scatter_rows_n_peer(const float* d_src, const int32_t* d_perm, int64_t n,
+                           const int32_t* d_n, int dim, float* const* d_seg_rows,
+                           int64_t capacity, kv_stream stream) {
+  return do_scatter_rows_n(d_src, d_perm, n, d_n, dim, nullptr, d_seg_rows, capacity, S(stream));
+}
+int kv_peer_barrier(uint32_t* const* d_peer_flags, uint32_t* d_my_flags, uint32_t* d_state,
+                    int rank, int world, int64_t timeout_ms, kv_stream stream) {
+  return do_peer_barrier(d_peer_flags, d_my_flags, d_state, rank, world, timeout_ms, S(stream));
 }
 int kv_unzip_pairs(const int64_t* d_pairs, int64_t n, int64_t* d_ids, int32_t* d_occ,
                    kv_stream stream) {
@@ -427,7 +456,7 @@ int kv_expand_rows(const float* d_src, const int32_t* d_perm, const int32_t* d_i
 }
 int kv_scatter_rows_n(const float* d_src, const int32_t* d_perm, int64_t n, const int32_t* d_n,
                       int dim, float* d_out, kv_stream stream) {
-  return do_scatter_rows_n(d_src, d_perm, n, d_n, dim, d_out, S(stream));
+  return do_scatter_rows_n(d_src, d_perm, n, d_n, dim, d_out, nullptr, 0, S(stream));
 }
 int kv_permute_rows(const float* d_src, const int32_t* d_perm, int64_t n, int dim, float* d_out,
                     kv_stream stream) {

@@ -425,12 +425,18 @@ partition_scatter_kernel(const long long* __restrict__ ids, long long n, const i
 // exchange that follows needs no host synchronisation and can be captured in a CUDA graph.
 // pairs != 0: send_ids holds interleaved {id, occurrence count} int64 pairs (one exchange
 // carries both); otherwise ids and counts go to two separate arrays.
+// dst != null (pairs only): shard g's row is the buffer dst[g] — peer g's inbox mapped over
+// NVLink — instead of send_ids + g * cap * 2, so routing and the id exchange are one kernel.
 __global__ void route_fill_kernel(long long* send_ids, int* send_occ, long long total, int* counts,
-                                  int num_shards, int pairs) {
+                                  int num_shards, int pairs, long long* const* __restrict__ dst,
+                                  int cap) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < total; j += stride) {
-    if (pairs) { send_ids[2 * j] = KEY_PAD; send_ids[2 * j + 1] = 0; }
+    if (dst) {
+      const long long g = j / cap;
+      reinterpret_cast<longlong2*>(dst[g])[j - g * cap] = make_longlong2(KEY_PAD, 0);
+    } else if (pairs) { send_ids[2 * j] = KEY_PAD; send_ids[2 * j + 1] = 0; }
     else {
       send_ids[j] = KEY_PAD;
       if (send_occ) send_occ[j] = 0;
@@ -455,7 +461,7 @@ route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ 
                      const int* d_n, int num_shards, int mode, int cap,
                      long long* __restrict__ send_ids, int* __restrict__ send_occ,
                      int* __restrict__ perm, int* __restrict__ counts, int* __restrict__ overflow,
-                     int pairs) {
+                     int pairs, long long* const* __restrict__ dst) {
   __shared__ int hist[MAX_SHARDS];
   __shared__ int basepos[MAX_SHARDS];
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
@@ -484,7 +490,9 @@ route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ 
         const int r = basepos[own[k]] + lr[k];
         if (r < cap) {
           const long long p = (long long)own[k] * cap + r;
-          if (pairs) {
+          if (dst) {
+            reinterpret_cast<longlong2*>(dst[own[k]])[r] = make_longlong2(ids[i], occ ? occ[i] : 1);
+          } else if (pairs) {
             reinterpret_cast<longlong2*>(send_ids)[p] = make_longlong2(ids[i], occ ? occ[i] : 1);
           } else {
             send_ids[p] = ids[i];
@@ -636,19 +644,22 @@ int do_partition_ids(Workspace* ws, const int64_t* ids, int64_t n, const int32_t
 int do_route_ids(Workspace* ws, const int64_t* ids, const int32_t* occ, int64_t n,
                  const int32_t* d_n, int num_shards, int mode, int cap, int64_t* send_ids,
                  int32_t* send_occ, int32_t* perm, int32_t* counts, int32_t* overflow, int pairs,
-                 cudaStream_t st) {
+                 int64_t* const* dst, cudaStream_t st) {
   if (num_shards < 1 || num_shards > MAX_SHARDS)
     return fail(1, "route_ids: num_shards must be in [1, 256]");
   if (cap < 1) return fail(1, "route_ids: capacity must be positive");
+  if (!send_ids && !dst) return fail(1, "route_ids: needs a send buffer or destination pointers");
   const int dev = ws->device;
   const long long total = (long long)num_shards * cap;
   route_fill_kernel<<<blocks_for(total, 256, dev), 256, 0, st>>>(
-      reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards, pairs);
+      reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards, pairs,
+      reinterpret_cast<long long* const*>(dst), cap);
   KV_LAUNCHED();
   if (n <= 0) return 0;
   route_scatter_kernel<<<blocks_for(n, 256 * 8, dev), 256, 0, st>>>(
       reinterpret_cast<const long long*>(ids), occ, n, d_n, num_shards, mode, cap,
-      reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow, pairs);
+      reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow, pairs,
+      reinterpret_cast<long long* const*>(dst));
   KV_LAUNCHED();
   return 0;
 }

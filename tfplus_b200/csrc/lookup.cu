@@ -42,14 +42,28 @@ constexpr int M_COPY = 1;    // row exists
 constexpr int M_FRESH = 2;   // being inserted by another thread of this launch
 constexpr int M_CLAIM = 3;   // this lane inserted the key and must fill the row
 
+template <bool SEG>
+__device__ __forceinline__ float* out_row(float* out, float* const* seg_out, int seg_len,
+                                          long long r, int dim) {
+  if (!SEG) return out + r * (long long)dim;
+  const long long g = r / seg_len;
+  return seg_out[g] + (r - g * seg_len) * (long long)dim;
+}
+
 // ---------------------------------------------------------------------------
 // KvVariable::FindOrInsert (kv_variable.h:263-380) when INSERT, else
 // KvVariable::FindOrZeros (kv_variable.h:239-254).
 // ---------------------------------------------------------------------------
-template <int VEC, int CPL, bool INSERT, int UQ>
+//
+// SEG: the output is `seg_len`-row segments living at seg_out[0], seg_out[1], … instead of one
+// array — the owner side of the shard exchange, where segment g is peer g's receive buffer
+// mapped over NVLink, so the lookup and the "rows back" transfer are one kernel.  Padding ids
+// are skipped outright there (their rows are never read by the requester).
+template <int VEC, int CPL, bool INSERT, int UQ, bool SEG>
 __global__ void __launch_bounds__(256)
 gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
-              long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags) {
+              long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags,
+              float* const* __restrict__ seg_out, int seg_len) {
   // A warp takes `kpw` ids (lanes < kpw probe): small kpw = more warps, so the machine is
   // full even for a 64 K-id batch and instruction latency hides behind other warps.
   constexpr int UNR = UQ / CPL > 0 ? UQ / CPL : 1;  // rows in flight per lane
@@ -84,7 +98,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
     uint32_t ctl = 0;
 
     if (valid && key == KEY_PAD) {
-      mode = M_ZERO;  // padding id of the shard exchange: zeros, no table access
+      mode = SEG ? M_SKIP : M_ZERO;  // padding id of the shard exchange: no table access
     } else if (valid) {
       Slot s;
       mode = M_ZERO;
@@ -168,7 +182,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         if (it + u < steps) {
           const int kl = (it + u) * kpi + tq;
           bool big = false;
-          float* op = out + (base + kl) * (long long)dim;
+          float* op = out_row<SEG>(out, seg_out, seg_len, base + kl, dim);
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             const int off = (q * tpr + tl) * VEC;
@@ -207,7 +221,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         long long r1, r2;
         init_rows_of(t, k, &r1, &r2);
         bool big = false;
-        float* op = out + (base + kl) * (long long)dim;
+        float* op = out_row<SEG>(out, seg_out, seg_len, base + kl, dim);
         for (int j = lane; j < nvec; j += 32) {
           Chunk<VEC> c;
           init_chunk<VEC>(t, r1, r2, j * VEC, c);
@@ -702,9 +716,12 @@ __global__ void expand_rows_kernel(const float* __restrict__ src, const int* __r
 }
 
 // out[perm[i],:] = src[i,:] for i < min(n, *d_n); rows with perm < 0 are dropped
+// seg_out != null: destination row p lives at seg_out[p / seg_len] + (p % seg_len) * dim
+// (the peers' receive buffers: the gradient exchange is this kernel's stores).
 __global__ void scatter_rows_n_kernel(const float* __restrict__ src, const int* __restrict__ perm,
                                       long long n, const int* __restrict__ d_n, int dim,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, float* const* __restrict__ seg_out,
+                                      int seg_len) {
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
   const int d4 = dim >> 2;
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -714,24 +731,28 @@ __global__ void scatter_rows_n_kernel(const float* __restrict__ src, const int* 
       const long long r = e / d4;
       const int c = (int)(e - r * d4);
       const long long p = perm[r];
-      if (p >= 0) reinterpret_cast<float4*>(out)[p * d4 + c] =
-          __ldg(reinterpret_cast<const float4*>(src) + r * d4 + c);
+      if (p < 0) continue;
+      float* o = seg_out ? out_row<true>(nullptr, seg_out, seg_len, p, dim) : out + p * dim;
+      reinterpret_cast<float4*>(o)[c] = __ldg(reinterpret_cast<const float4*>(src) + r * d4 + c);
     }
   } else {
     for (; e < n * dim; e += stride) {
       const long long r = e / dim;
       const int c = (int)(e - r * dim);
       const long long p = perm[r];
-      if (p >= 0) out[p * dim + c] = src[r * dim + c];
+      if (p < 0) continue;
+      float* o = seg_out ? out_row<true>(nullptr, seg_out, seg_len, p, dim) : out + p * dim;
+      o[c] = src[r * dim + c];
     }
   }
 }
 
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
-                  float* out, uint16_t today, cudaStream_t st, int tpr) {
+                  float* out, uint16_t today, cudaStream_t st, int tpr,
+                  float* const* seg_out = nullptr, int seg_len = 0) {
   static const int use_bulk = getenv("KVHBM_GATHER_BULK") ? atoi(getenv("KVHBM_GATHER_BULK")) : 0;
-  if (use_bulk && VEC == 4 && tb->dim * 4 <= 1024) {
+  if (use_bulk && !seg_out && VEC == 4 && tb->dim * 4 <= 1024) {
     // 4 warps x 32 rows of staging per block
     const int kpi = 32 / tpr;
     int kpw = 32;
@@ -770,8 +791,11 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
   const long long warps = (n + kpw - 1) / kpw;
   const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const long long* k = reinterpret_cast<const long long*>(ids);
-#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags)
-  if (insert) { if (uq == 4) KV_G(true, 4); else if (uq == 8) KV_G(true, 8); else KV_G(true, 16); }
+#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0)
+  if (seg_out) {
+    gather_kernel<VEC, CPL, true, 8, true><<<blocks, bs, 0, st>>>(
+        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len);
+  } else if (insert) { if (uq == 4) KV_G(true, 4); else if (uq == 8) KV_G(true, 8); else KV_G(true, 16); }
   else { if (uq == 4) KV_G(false, 4); else if (uq == 8) KV_G(false, 8); else KV_G(false, 16); }
 #undef KV_G
   KV_LAUNCHED();
@@ -835,6 +859,20 @@ int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts,
 #undef CALL
 }
 
+// FindOrInsert whose output rows land in per-segment buffers (peer memory): row r goes to
+// seg_out[r / seg_len] + (r % seg_len) * dim.  seg_out is a device array of device pointers.
+int do_gather_segments(Table* tb, const int64_t* ids, const int32_t* counts, int64_t n,
+                       float* const* seg_out, int64_t seg_len, uint16_t today, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (!seg_out || seg_len <= 0 || seg_len > 0x7fffffff)
+    return fail(1, "gather_segments: needs segment pointers and a positive segment length");
+  KV_TRY(tb->ensure(n, st));
+  RowGeom g = row_geom(tb->dim);
+#define CALL(V, C) launch_gather<V, C>(tb, true, ids, counts, n, nullptr, today, st, g.tpr, seg_out, (int)seg_len)
+  KV_DISPATCH_GEOM(g, CALL);
+#undef CALL
+}
+
 int do_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t n,
                cudaStream_t st) {
   if (n <= 0) return 0;
@@ -883,12 +921,16 @@ int do_expand_rows(const float* src, const int32_t* perm, const int32_t* idx, in
 }
 
 int do_scatter_rows_n(const float* src, const int32_t* perm, int64_t n, const int32_t* d_n,
-                      int dim, float* out, cudaStream_t st) {
+                      int dim, float* out, float* const* seg_out, int64_t seg_len,
+                      cudaStream_t st) {
   if (n <= 0) return 0;
+  if (!out && (!seg_out || seg_len <= 0))
+    return fail(1, "scatter_rows_n: needs an output array or segment pointers");
   int dev = 0;
   KV_CUDA(cudaGetDevice(&dev));
   const int64_t work = n * (int64_t)((dim & 3) == 0 ? dim / 4 : dim);
-  scatter_rows_n_kernel<<<blocks_for(work, 256, dev, 16), 256, 0, st>>>(src, perm, n, d_n, dim, out);
+  scatter_rows_n_kernel<<<blocks_for(work, 256, dev, 16), 256, 0, st>>>(
+      src, perm, n, d_n, dim, out, out ? nullptr : seg_out, (int)seg_len);
   KV_LAUNCHED();
   return 0;
 }

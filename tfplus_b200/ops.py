@@ -686,6 +686,45 @@ def scatter_rows_n(src, perm, n, num, out):
   return out
 
 
+# ---- peer-memory variants (include/kvhbm.h "Peer-memory"): `seg` is an int64 device tensor of
+# num_shards device pointers, normally into the peers' symmetric buffers ----
+def route_id_pairs_peer(ids, occ, num_shards, capacity, mode, num_ids, seg, out):
+  """kv_route_id_pairs_peer: pairs go to seg[g][0..capacity); out = dict(perm, counts, overflow)."""
+  ws = Workspace.get(ids.device)
+  with torch.cuda.device(ids.device):
+    check(_lib.load().kv_route_id_pairs_peer(ws.ptr, ids.data_ptr(), _ptr(occ), ids.numel(),
+                                             _ptr(num_ids), num_shards,
+                                             1 if mode == "mod" else 0, capacity, seg.data_ptr(),
+                                             out["perm"].data_ptr(), out["counts"].data_ptr(),
+                                             out["overflow"].data_ptr(), _stream(ids.device)))
+  return out
+
+
+def kv_variable_gather_or_insert_peer(table_handle, indices, counts, seg, capacity):
+  """KvVariableGatherOrInsertWithCounts whose row r lands in seg[r // capacity][r % capacity]."""
+  h = table_handle
+  ids = _ids(indices, h)
+  if ids.numel():
+    check(h._lib.kv_gather_or_insert_peer(h._live(), ids.data_ptr(), _ptr(counts), ids.numel(),
+                                          seg.data_ptr(), capacity, today(), h.stream))
+
+
+def scatter_rows_n_peer(src, perm, n, num, seg, capacity):
+  """seg[perm[i] // capacity][perm[i] % capacity] = src[i] for i < min(n, num[0])."""
+  with torch.cuda.device(src.device):
+    check(_lib.load().kv_scatter_rows_n_peer(src.data_ptr(), perm.data_ptr(), n, _ptr(num),
+                                             src.shape[1], seg.data_ptr(), capacity,
+                                             _stream(src.device)))
+
+
+def peer_barrier(peer_flags, my_flags, state, rank, world, timeout_ms=2000):
+  """kv_peer_barrier on the current stream of my_flags' device."""
+  with torch.cuda.device(my_flags.device):
+    check(_lib.load().kv_peer_barrier(peer_flags.data_ptr(), my_flags.data_ptr(),
+                                      state.data_ptr(), rank, world, timeout_ms,
+                                      _stream(my_flags.device)))
+
+
 def unique_into(ids, uniq, idx, counts, num):
   """kv_unique into caller-owned buffers (graph-capturable: nothing is allocated or read back)."""
   ws = Workspace.get(ids.device)

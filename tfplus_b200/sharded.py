@@ -16,6 +16,7 @@ is three exchanges over NVLink:
 The routing logic is backend-agnostic torch code: the product backend below is the CUDA one
 (tfplus_b200.ops -> C ABI); tests drive the same logic with world_size-2 gloo on CPU.
 """
+import math
 import os
 
 import torch
@@ -250,6 +251,125 @@ class PaddedShardedStep:
     return bool(self.route["overflow"].item())
 
 
+class PeerMemory:
+  """One symmetric allocation per GPU of the group, each mapped into every rank's address space
+  (torch symmetric memory: CUDA VMM handles exchanged through the process-group store).  Only
+  plumbing: the library sees raw device pointers."""
+
+  def __init__(self, nbytes, dev, group=None):
+    import torch.distributed._symmetric_memory as symm
+    group = group or dist.group.WORLD
+    self.buf = symm.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    self.buf.zero_()
+    self.hdl = symm.rendezvous(self.buf, group.group_name)
+    self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+    self.dev = dev
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)       # every rank's zero-fill is done before anybody stores
+
+  def local(self, offset, shape, dtype):
+    n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+    return self.buf[offset:offset + n].view(dtype).view(*shape)
+
+  def table(self, offset):
+    """Device array of every rank's `base + offset` (rank order)."""
+    return torch.tensor([p + int(offset) for p in self.ptrs], dtype=torch.int64, device=self.dev)
+
+
+class PeerShardedStep(PaddedShardedStep):
+  """PaddedShardedStep without NCCL in the data path: every exchange is the stores of the
+  kernel that produces the data, written straight into the destination GPU's buffer over
+  NVLink (kv_route_id_pairs_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the
+  only cross-GPU synchronisation is three kv_peer_barrier kernels per step.
+
+  Buffer reuse across steps needs no extra barrier: a rank stores into a peer's inbox / row /
+  gradient buffer only after a barrier that the peer reaches after its last read of the
+  previous step's contents (inbox: read before barrier 2, written after barrier 3 of the step
+  before; rows: read before barrier 3, written after barrier 1; gradients: read after barrier 3
+  and before the next barrier 1, written after barrier 1)."""
+
+  def __init__(self, *a, **kw):
+    super().__init__(*a, **kw)
+    t = torch
+    G, C, D, r = self.world, self.cap, self.dim, self.rank
+    al = lambda x: (x + 255) // 256 * 256
+    o_flags = 0
+    o_pairs = al(4 * G)
+    o_rows = o_pairs + al(G * C * 16)
+    o_grads = o_rows + al(G * C * D * 4)
+    total = o_grads + al(G * C * D * 4)
+    self.peer = PeerMemory(total, self.dev, self.group)
+    pm = self.peer
+    self.flags = pm.local(o_flags, (G,), t.int32)
+    self.pairs_in = pm.local(o_pairs, (G * C * 2,), t.int64)
+    self.rows_in = pm.local(o_rows, (G * C, D), t.float32)
+    self.grads_in = pm.local(o_grads, (G * C, D), t.float32)
+    self.seg_flags = pm.table(o_flags)
+    self.seg_pairs = pm.table(o_pairs + r * C * 16)
+    self.seg_rows = pm.table(o_rows + r * C * D * 4)
+    self.seg_grads = pm.table(o_grads + r * C * D * 4)
+    self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
+    self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
+
+  def _barrier(self):
+    ops.peer_barrier(self.seg_flags, self.flags, self.bstate, self.rank, self.world,
+                     self.barrier_ms)
+
+  def barrier_timeouts(self):
+    return int(self.bstate[1].item())
+
+  def run(self, ids, grad):
+    B, G, C, D = self.batch, self.world, self.cap, self.dim
+    t = torch
+    main = t.cuda.current_stream(self.dev)
+    side = self.side
+    # ---- forward: dedup; route = the id exchange; owner lookup = the row exchange ----
+    ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
+    ops.route_id_pairs_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_pairs,
+                            self.route)
+    side.wait_stream(main)
+    with t.cuda.stream(side):      # local half of the backward: sum duplicate gradients
+      ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
+    self._barrier()                # 1: every peer's pairs are in my inbox
+    ops.unzip_pairs(self.pairs_in, self.recv_ids, self.recv_occ)
+    ev_ids = t.cuda.Event()
+    ev_ids.record(main)
+    with t.cuda.stream(side):
+      side.wait_event(ev_ids)      # also: after barrier 1, so the owners are done with step-1 sums
+      ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads, C)
+      ops.unique_into(self.recv_ids, self.o_uniq, self.o_idx, None, self.o_num)
+      ops.zero_rows(self.o_gsum)
+    ops.kv_variable_gather_or_insert_peer(self.var, self.recv_ids, self.recv_occ, self.seg_rows, C)
+    self._barrier()                # 2: the rows I asked for are in rows_in
+    ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, self.out)
+    # ---- backward, owner half ----
+    main.wait_stream(side)
+    self._barrier()                # 3: every peer's gradient sums are in grads_in
+    ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
+                             accumulate=True)
+    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
+                                                   self.hpt, num_indices=self.o_num)
+    self.hpt[1:3].mul_(self.betas)
+    return self.out
+
+
+def make_padded_step(*a, **kw):
+  """The sync-free step over peer memory when the GPUs can map each other (KVHBM_SHARDED_P2P,
+  default on), else over NCCL all-to-alls.  Both are device paths; the choice is logged."""
+  import sys
+  want = os.environ.get("KVHBM_SHARDED_P2P", "1") != "0"
+  world = a[4] if len(a) > 4 else kw.get("world", 1)
+  if want and world > 1:
+    try:
+      return PeerShardedStep(*a, **kw)
+    except Exception as e:    # no P2P mapping on this box: say so, use the NCCL exchange
+      if os.environ.get("KVHBM_SHARDED_P2P") == "1":
+        raise
+      sys.stderr.write("[kvhbm] peer-memory exchange unavailable (%s: %s); using NCCL\n"
+                       % (type(e).__name__, e))
+  return PaddedShardedStep(*a, **kw)
+
+
 # ---------------------------------------------------------------------------
 # bench driver (bench.py --gpus N)
 # ---------------------------------------------------------------------------
@@ -310,8 +430,8 @@ class ShardedStepper:
     from . import _lib
     t = self.torch
     self.ids_d, self.grads_d = ids_d, grads_d
-    self.padded = PaddedShardedStep(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
-                                    self.world, self.rank, self.dev, self.hpt, self.betas)
+    self.padded = make_padded_step(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
+                                   self.world, self.rank, self.dev, self.hpt, self.betas)
     l0 = _lib.launch_count()
     for i in range(2):
       self.step_eager(ids_d[i], grads_d[i])
