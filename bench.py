@@ -265,17 +265,20 @@ def main_ours(args):
   note('prepared')
   for i in range(W):
     stepper.step(i)
+  # NVML is initialised BEFORE the barrier: a rank still inside nvmlInit when its peers start
+  # their timed loop shows up in their step time through the first exchange (this cost 20-60 %
+  # at N = 2..8 until it was found; the polling itself is harmless, scripts/sampler_probe.py).
+  # One sampler per node is enough.
+  clocks = ClockSampler(local_rank, enabled=(rank == 0),
+                        period_s=float(os.environ.get("KVHBM_BENCH_CLOCK_PERIOD_MS", "2")) * 1e-3)
   barrier()
-  # NVML queries take driver locks: with every rank polling, the ranks stall each other through
-  # the exchange (measured 2x on the 8-GPU step), so only rank 0 samples, and less often
-  all_ranks = os.environ.get("KVHBM_BENCH_CLOCK_RANKS", "0") == "all"
-  clocks = ClockSampler(local_rank, enabled=(rank == 0 or all_ranks),
-                        period_s=0.002 if world == 1 or all_ranks else 0.005)
   clocks.start()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
+  h0 = time.perf_counter()
   for i in range(K):
     stepper.step(i)
+  host_us = (time.perf_counter() - h0) / K * 1e6   # host time to enqueue one step
   e1.record()
   barrier()
   launches = K * stepper.launches_per_step   # graph replays: counted at capture time
@@ -349,6 +352,7 @@ def main_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "unique_per_step": u_meas, "clocks": clk, "gpu_launches": int(launches),
+        "host_enqueue_us_per_step": host_us,
         "e2e": {"value": e2e_val, "unit": UNIT,
                 "h2d_bytes_per_step": int(B * 8 + B * D * 4),
                 "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K},
