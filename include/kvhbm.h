@@ -280,11 +280,12 @@ int kv_scatter_rows(const float* d_src, const int32_t* d_perm, int64_t n, int di
  * `d_seg` argument is a DEVICE array of num_shards device pointers; segment g
  * holds `capacity` entries and normally points at peer g's buffer + rank * capacity.
  * Replaces the PS<->worker send/recv around the ops of SURVEY.md §8e.          */
-/* kv_route_id_pairs whose {id, count} pairs go straight to d_seg_pairs[g][0..capacity). */
-int kv_route_id_pairs_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ,
-                           int64_t n, const int32_t* d_n, int num_shards, int mode, int capacity,
-                           int64_t* const* d_seg_pairs, int32_t* d_perm, int32_t* d_counts,
-                           int32_t* d_overflow, kv_stream stream);
+/* kv_route_ids whose ids / occurrence counts go straight to d_seg_ids[g][0..capacity) /
+ * d_seg_occ[g][0..capacity) (padding included). */
+int kv_route_ids_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                      const int32_t* d_n, int num_shards, int mode, int capacity,
+                      int64_t* const* d_seg_ids, int32_t* const* d_seg_occ, int32_t* d_perm,
+                      int32_t* d_counts, int32_t* d_overflow, kv_stream stream);
 /* kv_gather_or_insert whose row r is written to d_seg_rows[r / capacity] + (r % capacity) * dim;
  * rows of padding ids are not written at all. */
 int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,

@@ -17,7 +17,7 @@ st.populate()
 ids_np, g_np = bench.make_batches(4, keys * world, bench.BATCH, bench.DIM, seed_ids=2024 + rank, seed_grad=7 + rank)
 ids = [torch.from_numpy(x).to(dev) for x in ids_np]
 gr = [torch.from_numpy(x).to(dev) for x in g_np]
-os.environ["KVHBM_SHARDED_GRAPH"] = "0"
+os.environ.setdefault("KVHBM_SHARDED_GRAPH", "0")
 st.prepare(ids, gr)
 for i in range(5): st.step(i)
 torch.cuda.synchronize(); dist.barrier()
@@ -34,4 +34,20 @@ if rank == 0:
   tot = sum(r[0] for r in rows)
   print("kernel time per step: %.1f us" % tot)
   for r in rows[:25]: print("%8.1f us  x%.1f  %s" % r)
+if rank == 0:
+  # timeline of the last two steps: start (us, relative), duration, stream, kernel
+  import json, tempfile
+  path = os.path.join(tempfile.gettempdir(), "kv_trace_%d.json" % os.getpid())
+  prof.export_chrome_trace(path)
+  ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+  ev.sort(key=lambda e: e["ts"])
+  per_step = max(1, len(ev) // 10)
+  tail = ev[-2 * per_step:]
+  t0 = tail[0]["ts"]
+  print("timeline (last 2 steps, %d kernels per step):" % per_step)
+  for e in tail:
+    print("%8.1f +%6.1f us  s%-3s %s" % (e["ts"] - t0, e["dur"], e["args"].get("stream", "?"),
+                                        e["name"][:60]))
+st.release()
+torch.cuda.synchronize()
 dist.barrier(); dist.destroy_process_group()

@@ -44,7 +44,7 @@ int do_partition_ids(Workspace*, const int64_t*, int64_t, const int32_t*, int, i
 
 int do_route_ids(Workspace*, const int64_t*, const int32_t*, int64_t, const int32_t*, int, int, int,
                  int64_t*, int32_t*, int32_t*, int32_t*, int32_t*, int pairs, int64_t* const*,
-                 cudaStream_t);
+                 int32_t* const*, cudaStream_t);
 int do_gather_segments(Table*, const int64_t*, const int32_t*, int64_t, float* const*, int64_t,
                        uint16_t, cudaStream_t);
 int do_peer_barrier(uint32_t* const*, uint32_t*, uint32_t*, int, int, int64_t, cudaStream_t);
@@ -410,7 +410,7 @@ int kv_route_ids(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, i
   KV_NEED(ws && d_send_ids && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
           "route_ids: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_ids,
-                      d_send_occ, d_perm, d_counts, d_overflow, /*pairs=*/0, nullptr, S(stream));
+                      d_send_occ, d_perm, d_counts, d_overflow, /*pairs=*/0, nullptr, nullptr, S(stream));
 }
 int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
                       const int32_t* d_n, int num_shards, int mode, int capacity,
@@ -419,16 +419,16 @@ int kv_route_id_pairs(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_o
   KV_NEED(ws && d_send_pairs && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
           "route_id_pairs: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, d_send_pairs,
-                      nullptr, d_perm, d_counts, d_overflow, /*pairs=*/1, nullptr, S(stream));
+                      nullptr, d_perm, d_counts, d_overflow, /*pairs=*/1, nullptr, nullptr, S(stream));
 }
-int kv_route_id_pairs_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ,
-                           int64_t n, const int32_t* d_n, int num_shards, int mode, int capacity,
-                           int64_t* const* d_seg_pairs, int32_t* d_perm, int32_t* d_counts,
-                           int32_t* d_overflow, kv_stream stream) {
-  KV_NEED(ws && d_seg_pairs && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
-          "route_id_pairs_peer: bad arguments");
+int kv_route_ids_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_occ, int64_t n,
+                      const int32_t* d_n, int num_shards, int mode, int capacity,
+                      int64_t* const* d_seg_ids, int32_t* const* d_seg_occ, int32_t* d_perm,
+                      int32_t* d_counts, int32_t* d_overflow, kv_stream stream) {
+  KV_NEED(ws && d_seg_ids && d_seg_occ && d_counts && d_overflow && (n == 0 || (d_ids && d_perm)),
+          "route_ids_peer: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, nullptr, nullptr,
-                      d_perm, d_counts, d_overflow, /*pairs=*/1, d_seg_pairs, S(stream));
+                      d_perm, d_counts, d_overflow, /*pairs=*/0, d_seg_ids, d_seg_occ, S(stream));
 }
 int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
                              int64_t n, float* const* d_seg_rows, int64_t capacity,

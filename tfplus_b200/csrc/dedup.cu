@@ -40,8 +40,8 @@ constexpr int UB = 1024;  // ids per block in the scan kernels (256 threads x 4)
 
 struct __align__(16) USlot {
   long long key;
-  int first;  // smallest position holding this key
-  int rank;   // index among the unique keys
+  int first;  // smallest position holding this key; once ranked, ~rank (negative)
+  int count;  // occurrences of the key
 };
 
 // unique() keeps TWO scratch hash tables and alternates between them: the last kernel of a
@@ -78,10 +78,13 @@ __global__ void unique_wipe_kernel(UScratch s) {
 
 // One probe per distinct id of a warp: the copies of a hot id inside a warp elect a leader
 // (match.any), so a Zipf head id costs one 64-bit CAS per warp instead of one per occurrence,
-// and the atomicMin is skipped once an earlier position is already recorded.
+// and the atomicMin is skipped once an earlier position is already recorded.  Occurrences are
+// counted here too, one fire-and-forget add per (warp, distinct id): counting per occurrence
+// in the index kernel serialised ~7 500 adds on the head id's counter (13 us of a 29 us call).
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
-                     int* __restrict__ slot_of, int* __restrict__ counts) {
+                     int* __restrict__ slot_of) {
   USlot* tab = s.tab[s.sel[0] & 1];
   const unsigned long long mask = s.cap - 1;
   const int lane = threadIdx.x & 31;
@@ -93,7 +96,6 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
     const long long key = valid ? ids[i] : 0;
     const unsigned active = __ballot_sync(0xffffffffu, valid);
     if (!valid) continue;
-    if (counts) counts[i] = 0;  // incremented two kernels later
     const unsigned peers = __match_any_sync(active, key);
     const int leader = __ffs(peers) - 1;  // lowest lane = smallest position
     unsigned long long pos = 0;
@@ -111,6 +113,7 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
         pos = (pos + 1) & mask;
       }
       if (__ldcg(&tab[pos].first) > (int)i) atomicMin(&tab[pos].first, (int)i);
+      if (COUNT) atomicAdd(&tab[pos].count, __popc(peers));
     }
     pos = __shfl_sync(peers, pos, leader);
     slot_of[i] = (int)pos;
@@ -124,7 +127,8 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
 __global__ void __launch_bounds__(256)
 unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
                    const long long* __restrict__ ids, long long n,
-                   long long* __restrict__ uniq, int* __restrict__ num_unique) {
+                   long long* __restrict__ uniq, int* __restrict__ counts,
+                   int* __restrict__ num_unique) {
   __shared__ int warp_tot[8];
   __shared__ int block_prefix;
   const int which = sc.sel[0] & 1;
@@ -185,8 +189,11 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (f[k]) {
+      // the other occurrences only test first == their own position: ~r is negative, so
+      // overwriting first with the rank cannot turn any of them into a first occurrence
       uniq[r] = ids[i0 + k];
-      tab[s[k]].rank = r;
+      if (counts) counts[r] = tab[s[k]].count;
+      tab[s[k]].first = ~r;
       ++r;
     }
   }
@@ -194,15 +201,13 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
 
 // idx[i] = rank of id i's slot; the same launch wipes the other table for the next call.
 __global__ void unique_index_kernel(UScratch s, const int* __restrict__ slot_of, long long n,
-                                    int* __restrict__ idx, int* __restrict__ counts) {
+                                    int* __restrict__ idx) {
   const int which = s.sel[1] & 1;
   const USlot* __restrict__ tab = s.tab[which];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < n; j += stride) {
-    const int r = tab[slot_of[j]].rank;
-    idx[j] = r;
-    if (counts) atomicAdd(&counts[r], 1);
+    idx[j] = ~tab[slot_of[j]].first;
   }
   // NB: the table just used stays dirty until the call after next wipes it
   wipe(s.tab[which ^ 1], s.cap, s.status[which ^ 1], s.nb_max, (unsigned long long)i,
@@ -425,17 +430,19 @@ partition_scatter_kernel(const long long* __restrict__ ids, long long n, const i
 // exchange that follows needs no host synchronisation and can be captured in a CUDA graph.
 // pairs != 0: send_ids holds interleaved {id, occurrence count} int64 pairs (one exchange
 // carries both); otherwise ids and counts go to two separate arrays.
-// dst != null (pairs only): shard g's row is the buffer dst[g] — peer g's inbox mapped over
-// NVLink — instead of send_ids + g * cap * 2, so routing and the id exchange are one kernel.
+// dst_ids != null: shard g's row lives at dst_ids[g] / dst_occ[g] — peer g's inbox mapped over
+// NVLink — instead of send_ids + g * cap, so routing and the id exchange are one kernel.
 __global__ void route_fill_kernel(long long* send_ids, int* send_occ, long long total, int* counts,
-                                  int num_shards, int pairs, long long* const* __restrict__ dst,
-                                  int cap) {
+                                  int num_shards, int pairs,
+                                  long long* const* __restrict__ dst_ids,
+                                  int* const* __restrict__ dst_occ, int cap) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < total; j += stride) {
-    if (dst) {
+    if (dst_ids) {
       const long long g = j / cap;
-      reinterpret_cast<longlong2*>(dst[g])[j - g * cap] = make_longlong2(KEY_PAD, 0);
+      dst_ids[g][j - g * cap] = KEY_PAD;
+      dst_occ[g][j - g * cap] = 0;
     } else if (pairs) { send_ids[2 * j] = KEY_PAD; send_ids[2 * j + 1] = 0; }
     else {
       send_ids[j] = KEY_PAD;
@@ -456,22 +463,28 @@ __global__ void unzip_pairs_kernel(const long long* __restrict__ pairs, long lon
   }
 }
 
+constexpr int ROUTE_K = 2;
+
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ occ, long long n,
                      const int* d_n, int num_shards, int mode, int cap,
                      long long* __restrict__ send_ids, int* __restrict__ send_occ,
                      int* __restrict__ perm, int* __restrict__ counts, int* __restrict__ overflow,
-                     int pairs, long long* const* __restrict__ dst) {
+                     int pairs, long long* const* __restrict__ dst_ids,
+                     int* const* __restrict__ dst_occ) {
   __shared__ int hist[MAX_SHARDS];
   __shared__ int basepos[MAX_SHARDS];
   if (d_n) { long long dn = *d_n; if (dn < n) n = dn; }
-  const long long per_block = 256 * 8;
+  // 2 ids per thread: the kernel is a chain of dependent phases (load, shared histogram,
+  // one global add per shard, stores), so it wants many small blocks, not few long ones
+  constexpr int K = ROUTE_K;
+  const long long per_block = 256 * K;
   for (long long b0 = blockIdx.x * per_block; b0 < n; b0 += gridDim.x * per_block) {
     for (int g = threadIdx.x; g < num_shards; g += blockDim.x) hist[g] = 0;
     __syncthreads();
-    int own[8], lr[8];
+    int own[K], lr[K];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < K; ++k) {
       const long long i = b0 + k * 256 + threadIdx.x;
       own[k] = -1;
       if (i < n) {
@@ -484,14 +497,15 @@ route_scatter_kernel(const long long* __restrict__ ids, const int* __restrict__ 
       basepos[g] = hist[g] ? atomicAdd(&counts[g], hist[g]) : 0;
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < K; ++k) {
       const long long i = b0 + k * 256 + threadIdx.x;
       if (own[k] >= 0) {
         const int r = basepos[own[k]] + lr[k];
         if (r < cap) {
           const long long p = (long long)own[k] * cap + r;
-          if (dst) {
-            reinterpret_cast<longlong2*>(dst[own[k]])[r] = make_longlong2(ids[i], occ ? occ[i] : 1);
+          if (dst_ids) {
+            dst_ids[own[k]][r] = ids[i];
+            dst_occ[own[k]][r] = occ ? occ[i] : 1;
           } else if (pairs) {
             reinterpret_cast<longlong2*>(send_ids)[p] = make_longlong2(ids[i], occ ? occ[i] : 1);
           } else {
@@ -567,13 +581,14 @@ int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32
     KV_LAUNCHED();
     ws_mark_wiped(ws);
   }
-  unique_insert_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of, counts);
+  if (counts) unique_insert_kernel<true><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
+  else unique_insert_kernel<false><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
   KV_LAUNCHED();
   unique_rank_kernel<<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
-                                         num_unique);
+                                         counts, num_unique);
   KV_LAUNCHED();
   const long long span = n > (long long)sc.cap ? n : (long long)sc.cap;
-  unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx, counts);
+  unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx);
   KV_LAUNCHED();
   return 0;
 }
@@ -644,22 +659,23 @@ int do_partition_ids(Workspace* ws, const int64_t* ids, int64_t n, const int32_t
 int do_route_ids(Workspace* ws, const int64_t* ids, const int32_t* occ, int64_t n,
                  const int32_t* d_n, int num_shards, int mode, int cap, int64_t* send_ids,
                  int32_t* send_occ, int32_t* perm, int32_t* counts, int32_t* overflow, int pairs,
-                 int64_t* const* dst, cudaStream_t st) {
+                 int64_t* const* dst_ids, int32_t* const* dst_occ, cudaStream_t st) {
   if (num_shards < 1 || num_shards > MAX_SHARDS)
     return fail(1, "route_ids: num_shards must be in [1, 256]");
   if (cap < 1) return fail(1, "route_ids: capacity must be positive");
-  if (!send_ids && !dst) return fail(1, "route_ids: needs a send buffer or destination pointers");
+  if (!send_ids && !(dst_ids && dst_occ))
+    return fail(1, "route_ids: needs a send buffer or destination pointers");
   const int dev = ws->device;
   const long long total = (long long)num_shards * cap;
   route_fill_kernel<<<blocks_for(total, 256, dev), 256, 0, st>>>(
       reinterpret_cast<long long*>(send_ids), send_occ, total, counts, num_shards, pairs,
-      reinterpret_cast<long long* const*>(dst), cap);
+      reinterpret_cast<long long* const*>(dst_ids), dst_occ, cap);
   KV_LAUNCHED();
   if (n <= 0) return 0;
-  route_scatter_kernel<<<blocks_for(n, 256 * 8, dev), 256, 0, st>>>(
+  route_scatter_kernel<<<blocks_for(n, 256 * ROUTE_K, dev), 256, 0, st>>>(
       reinterpret_cast<const long long*>(ids), occ, n, d_n, num_shards, mode, cap,
       reinterpret_cast<long long*>(send_ids), send_occ, perm, counts, overflow, pairs,
-      reinterpret_cast<long long* const*>(dst));
+      reinterpret_cast<long long* const*>(dst_ids), dst_occ);
   KV_LAUNCHED();
   return 0;
 }

@@ -688,15 +688,16 @@ def scatter_rows_n(src, perm, n, num, out):
 
 # ---- peer-memory variants (include/kvhbm.h "Peer-memory"): `seg` is an int64 device tensor of
 # num_shards device pointers, normally into the peers' symmetric buffers ----
-def route_id_pairs_peer(ids, occ, num_shards, capacity, mode, num_ids, seg, out):
-  """kv_route_id_pairs_peer: pairs go to seg[g][0..capacity); out = dict(perm, counts, overflow)."""
+def route_ids_peer(ids, occ, num_shards, capacity, mode, num_ids, seg_ids, seg_occ, out):
+  """kv_route_ids_peer: ids / counts go to seg_ids[g][0..capacity) / seg_occ[g][0..capacity);
+  out = dict(perm, counts, overflow)."""
   ws = Workspace.get(ids.device)
   with torch.cuda.device(ids.device):
-    check(_lib.load().kv_route_id_pairs_peer(ws.ptr, ids.data_ptr(), _ptr(occ), ids.numel(),
-                                             _ptr(num_ids), num_shards,
-                                             1 if mode == "mod" else 0, capacity, seg.data_ptr(),
-                                             out["perm"].data_ptr(), out["counts"].data_ptr(),
-                                             out["overflow"].data_ptr(), _stream(ids.device)))
+    check(_lib.load().kv_route_ids_peer(ws.ptr, ids.data_ptr(), _ptr(occ), ids.numel(),
+                                        _ptr(num_ids), num_shards, 1 if mode == "mod" else 0,
+                                        capacity, seg_ids.data_ptr(), seg_occ.data_ptr(),
+                                        out["perm"].data_ptr(), out["counts"].data_ptr(),
+                                        out["overflow"].data_ptr(), _stream(ids.device)))
   return out
 
 

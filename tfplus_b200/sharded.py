@@ -279,14 +279,18 @@ class PeerMemory:
 class PeerShardedStep(PaddedShardedStep):
   """PaddedShardedStep without NCCL in the data path: every exchange is the stores of the
   kernel that produces the data, written straight into the destination GPU's buffer over
-  NVLink (kv_route_id_pairs_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the
-  only cross-GPU synchronisation is three kv_peer_barrier kernels per step.
+  NVLink (kv_route_ids_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the only
+  cross-GPU synchronisation is two kv_peer_barrier kernels per step:
 
-  Buffer reuse across steps needs no extra barrier: a rank stores into a peer's inbox / row /
-  gradient buffer only after a barrier that the peer reaches after its last read of the
-  previous step's contents (inbox: read before barrier 2, written after barrier 3 of the step
-  before; rows: read before barrier 3, written after barrier 1; gradients: read after barrier 3
-  and before the next barrier 1, written after barrier 1)."""
+    unique -> route ==ids==> | barrier A | owner lookup ==rows==>      | barrier B | expand rows
+           -> local grad sums            | grad sums    ==grads==>     |           | owner sum, apply
+                                         | owner-side dedup            |
+
+  (ids and gradients are both inputs of the step, as in the single-GPU step, so the gradient
+  exchange shares barrier B with the rows.)  Buffer reuse across steps needs no extra barrier:
+  a rank stores into a peer's inbox only after barrier B of the step before, which the peer
+  reaches after its last read of the inbox; into a peer's row / gradient buffers only after
+  barrier A, which the peer reaches after the previous step's expand / owner sum."""
 
   def __init__(self, *a, **kw):
     super().__init__(*a, **kw)
@@ -294,22 +298,27 @@ class PeerShardedStep(PaddedShardedStep):
     G, C, D, r = self.world, self.cap, self.dim, self.rank
     al = lambda x: (x + 255) // 256 * 256
     o_flags = 0
-    o_pairs = al(4 * G)
-    o_rows = o_pairs + al(G * C * 16)
+    o_ids = al(4 * G)
+    o_occ = o_ids + al(G * C * 8)
+    o_rows = o_occ + al(G * C * 4)
     o_grads = o_rows + al(G * C * D * 4)
     total = o_grads + al(G * C * D * 4)
     self.peer = PeerMemory(total, self.dev, self.group)
     pm = self.peer
     self.flags = pm.local(o_flags, (G,), t.int32)
-    self.pairs_in = pm.local(o_pairs, (G * C * 2,), t.int64)
+    self.ids_in = pm.local(o_ids, (G * C,), t.int64)
+    self.occ_in = pm.local(o_occ, (G * C,), t.int32)
     self.rows_in = pm.local(o_rows, (G * C, D), t.float32)
     self.grads_in = pm.local(o_grads, (G * C, D), t.float32)
     self.seg_flags = pm.table(o_flags)
-    self.seg_pairs = pm.table(o_pairs + r * C * 16)
+    self.seg_ids = pm.table(o_ids + r * C * 8)
+    self.seg_occ = pm.table(o_occ + r * C * 4)
     self.seg_rows = pm.table(o_rows + r * C * D * 4)
     self.seg_grads = pm.table(o_grads + r * C * D * 4)
     self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
+    self.side2 = t.cuda.Stream(device=self.dev)
+    self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
 
   def _barrier(self):
     ops.peer_barrier(self.seg_flags, self.flags, self.bstate, self.rank, self.world,
@@ -322,34 +331,42 @@ class PeerShardedStep(PaddedShardedStep):
     B, G, C, D = self.batch, self.world, self.cap, self.dim
     t = torch
     main = t.cuda.current_stream(self.dev)
-    side = self.side
-    # ---- forward: dedup; route = the id exchange; owner lookup = the row exchange ----
+    s1, s2 = self.side, self.side2
     ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
-    ops.route_id_pairs_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_pairs,
-                            self.route)
-    side.wait_stream(main)
-    with t.cuda.stream(side):      # local half of the backward: sum duplicate gradients
+    s2.wait_stream(main)
+    with t.cuda.stream(s2):        # sum duplicate gradients locally
       ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
-    self._barrier()                # 1: every peer's pairs are in my inbox
-    ops.unzip_pairs(self.pairs_in, self.recv_ids, self.recv_occ)
-    ev_ids = t.cuda.Event()
-    ev_ids.record(main)
-    with t.cuda.stream(side):
-      side.wait_event(ev_ids)      # also: after barrier 1, so the owners are done with step-1 sums
+    # route = the id exchange: ids / counts land in the owners' inboxes
+    ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids, self.seg_occ,
+                       self.route)
+    self._barrier()                # A: every peer's ids are in my inbox
+    ev_a = t.cuda.Event()
+    ev_a.record(main)
+    with t.cuda.stream(s1):        # owner-side dedup of what the peers sent
+      s1.wait_event(ev_a)
+      ops.unique_into(self.ids_in, self.o_uniq, self.o_idx, None, self.o_num)
+    with t.cuda.stream(s2):        # gradient exchange: sums go to the owners' buffers
+      s2.wait_event(ev_a)
       ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads, C)
-      ops.unique_into(self.recv_ids, self.o_uniq, self.o_idx, None, self.o_num)
       ops.zero_rows(self.o_gsum)
-    ops.kv_variable_gather_or_insert_peer(self.var, self.recv_ids, self.recv_occ, self.seg_rows, C)
-    self._barrier()                # 2: the rows I asked for are in rows_in
-    ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, self.out)
-    # ---- backward, owner half ----
-    main.wait_stream(side)
-    self._barrier()                # 3: every peer's gradient sums are in grads_in
+    # owner lookup = the row exchange: rows land in the requesters' buffers
+    ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in, self.occ_in, self.seg_rows, C)
+    main.wait_stream(s1)
+    main.wait_stream(s2)
+    self._barrier()                # B: my rows and every peer's gradient sums have arrived
+    ev_b = t.cuda.Event()
+    ev_b.record(main)
+    # the longer branch is issued first: a captured graph keeps the first dependent of a node
+    # on the node's own stream and pays ~5 us of cross-stream latency for the others
     ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
                              accumulate=True)
     ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
                                                    self.hpt, num_indices=self.o_num)
     self.hpt[1:3].mul_(self.betas)
+    with t.cuda.stream(s1):
+      s1.wait_event(ev_b)
+      ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, self.out)
+    main.wait_stream(s1)
     return self.out
 
 
