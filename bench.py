@@ -365,11 +365,12 @@ def main_ours(args):
         raise SystemExit("peer barrier timed out %d times: the step is invalid"
                          % stepper.padded.barrier_timeouts())
       line["nvlink"] = {"exchange": "peer-memory stores fused into the producing kernels + "
-                                    "3 barrier kernels" if peer else "NCCL all_to_all_single x3",
+                                    "2 barrier kernels" if peer else "NCCL all_to_all_single x3",
                         "bytes_sent_per_gpu_per_step": sent,
                         "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
                         "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
-                        "exchanges_per_step": 3, "capacity_per_peer": stepper.padded.cap,
+                        "exchanges_per_step": 3, "barriers_per_step": 2 if peer else None,
+                        "capacity_per_peer": stepper.padded.cap,
                         "overflowed": stepper.padded.overflowed(),
                         "note": "fixed-capacity exchange of {id, occurrence count} pairs, rows, "
                                 "gradients (bytes = capacity upper bound), captured with the "

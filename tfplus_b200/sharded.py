@@ -203,7 +203,7 @@ class PaddedShardedStep:
     else:
       dist.all_to_all_single(out, inp, group=self.group)
 
-  def run(self, ids, grad):
+  def run(self, ids, grad, out=None):
     """All NCCL calls stay on the calling stream in a fixed order; work that only depends on
     the ids (local gradient sum, the owner-side dedup) runs on a side stream underneath the
     exchanges and is joined where its result is needed."""
@@ -236,7 +236,8 @@ class PaddedShardedStep:
     ops.kv_variable_gather_or_insert_with_counts(self.var, self.recv_ids, self.recv_occ,
                                                  out=self.rows_owner)
     self._a2a(self.rows_recv, self.rows_owner)
-    ops.expand_rows(self.rows_recv, self.route["perm"], self.idx, B, self.out)
+    out = self.out if out is None else out
+    ops.expand_rows(self.rows_recv, self.route["perm"], self.idx, B, out)
     # ---- backward: route gradients, owner merge, fused apply ----
     main.wait_stream(side)
     self._a2a(self.g_recv, self.g_send)
@@ -245,7 +246,7 @@ class PaddedShardedStep:
     ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
                                                    self.hpt, num_indices=self.o_num)
     self.hpt[1:3].mul_(self.betas)
-    return self.out
+    return out
 
   def overflowed(self):
     return bool(self.route["overflow"].item())
@@ -327,9 +328,10 @@ class PeerShardedStep(PaddedShardedStep):
   def barrier_timeouts(self):
     return int(self.bstate[1].item())
 
-  def run(self, ids, grad):
+  def run(self, ids, grad, out=None):
     B, G, C, D = self.batch, self.world, self.cap, self.dim
     t = torch
+    out = self.out if out is None else out
     main = t.cuda.current_stream(self.dev)
     s1, s2 = self.side, self.side2
     ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
@@ -365,9 +367,9 @@ class PeerShardedStep(PaddedShardedStep):
     self.hpt[1:3].mul_(self.betas)
     with t.cuda.stream(s1):
       s1.wait_event(ev_b)
-      ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, self.out)
+      ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, out)
     main.wait_stream(s1)
-    return self.out
+    return out
 
 
 def make_padded_step(*a, **kw):
@@ -481,6 +483,7 @@ class ShardedStepper:
 
   def release(self):
     self.graphs = []
+    self.e2e = []
 
   def stage_times(self, steps):
     t = self.torch
@@ -493,19 +496,73 @@ class ShardedStepper:
     t.cuda.synchronize()
     return {"sharded step": a.elapsed_time(b) / steps}
 
+  def _capture(self, fn):
+    t = self.torch
+    if os.environ.get("KVHBM_SHARDED_GRAPH", "1") == "0":
+      return None
+    side = t.cuda.Stream(device=self.dev)
+    side.wait_stream(t.cuda.current_stream(self.dev))
+    with t.cuda.stream(side):
+      g = t.cuda.CUDAGraph()
+      with t.cuda.graph(g, stream=side):
+        fn()
+    t.cuda.current_stream(self.dev).wait_stream(side)
+    return g
+
   def prepare_host(self, ids_h, grads_h, rows_h):
+    """End to end: every step copies its ids + gradients from pinned host memory and its rows
+    back.  Two input / output slots and two copy streams, so the H2D of step i+1 and the D2H
+    of step i-1 run under the kernels and exchanges of step i; every copy still happens once
+    per step inside the timed region."""
     t = self.torch
     self.ids_h, self.grads_h, self.rows_h = ids_h, grads_h, rows_h
-    self.h_ids = t.empty(self.batch, dtype=t.int64, device=self.dev)
-    self.h_grad = t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+    self.s_h2d, self.s_d2h = t.cuda.Stream(device=self.dev), t.cuda.Stream(device=self.dev)
+    self.h_ids = [t.empty(self.batch, dtype=t.int64, device=self.dev) for _ in range(2)]
+    self.h_grad = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                   for _ in range(2)]
+    self.h_out = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                  for _ in range(2)]
+    self.rows_host = [rows_h, t.empty_like(rows_h).pin_memory()]
+    self.ev_in = [t.cuda.Event() for _ in range(2)]
+    self.ev_done = [t.cuda.Event() for _ in range(2)]
+    self.ev_out = [t.cuda.Event() for _ in range(2)]
+    for k in range(2):
+      self.h_ids[k].copy_(ids_h[k])
+      self.h_grad[k].copy_(grads_h[k])
+    t.cuda.synchronize()
+    self.e2e = [self._capture(lambda k=k: self.padded.run(self.h_ids[k], self.h_grad[k],
+                                                          out=self.h_out[k])) for k in range(2)]
+    main = t.cuda.current_stream(self.dev)
+    for k in range(2):
+      self.ev_done[k].record(main)
+      self.ev_out[k].record(main)
+    self.e2e_i = 0
 
   def finish_host(self):
-    pass
+    main = self.torch.cuda.current_stream(self.dev)
+    main.wait_stream(self.s_h2d)
+    main.wait_stream(self.s_d2h)
 
   def step_host(self, i):
-    k = i % len(self.ids_h)
-    self.h_ids.copy_(self.ids_h[k], non_blocking=True)
-    self.h_grad.copy_(self.grads_h[k], non_blocking=True)
-    rows = self.padded.run(self.h_ids, self.h_grad)
+    t = self.torch
+    k = self.e2e_i & 1
+    self.e2e_i += 1
+    j = i % len(self.ids_h)
+    main = t.cuda.current_stream(self.dev)
+    with t.cuda.stream(self.s_h2d):
+      self.s_h2d.wait_event(self.ev_done[k])       # slot k's previous step no longer reads it
+      self.h_ids[k].copy_(self.ids_h[j], non_blocking=True)
+      self.h_grad[k].copy_(self.grads_h[j], non_blocking=True)
+      self.ev_in[k].record(self.s_h2d)
+    main.wait_event(self.ev_in[k])
+    main.wait_event(self.ev_out[k])                # slot k's rows have been drained to the host
+    if self.e2e[k] is not None:
+      self.e2e[k].replay()
+    else:
+      self.padded.run(self.h_ids[k], self.h_grad[k], out=self.h_out[k])
     self.steps_done += 1
-    self.rows_h.copy_(rows, non_blocking=True)
+    self.ev_done[k].record(main)
+    with t.cuda.stream(self.s_d2h):
+      self.s_d2h.wait_event(self.ev_done[k])
+      self.rows_host[k].copy_(self.h_out[k], non_blocking=True)
+      self.ev_out[k].record(self.s_d2h)
