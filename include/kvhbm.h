@@ -168,6 +168,16 @@ int kv_apply_sparse_group_ftrl_dev(kv_table* var, kv_table* accum, kv_table* lin
 int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids,
                       const float* d_grad, int64_t n, const int32_t* d_n,
                       const float* d_hp, uint16_t today, kv_stream stream);
+/* The `_dev` apply plus AdamOptimizer._finish in the same launch: once every row is updated,
+ * beta1_power *= beta1 and beta2_power *= beta2 inside d_hp (group_adam.py inherits _finish
+ * from tf.train.AdamOptimizer; python/training/adam.py keeps the powers as non-slot variables),
+ * so a training step needs no separate scalar-update op between two applies. */
+int kv_apply_group_adam_v4_dev_advance(kv_table* var, kv_table* m_v_linear, const int64_t* d_ids,
+                                       const float* d_grad, int64_t n, const int32_t* d_n,
+                                       float* d_hp, uint16_t today, kv_stream stream);
+int kv_apply_adam_dev_advance(kv_table* var, kv_table* m_v, const int64_t* d_ids,
+                              const float* d_grad, int64_t n, const int32_t* d_n, float* d_hp,
+                              uint16_t today, kv_stream stream);
 
 /* ---- dedup (stock TF ops on the path; TF 2.13 Unique / UnsortedSegmentSum) */
 

@@ -284,6 +284,34 @@ def test_fused_adam_matches_scatter_path():
   mv.check_state()
 
 
+@pytest.mark.parametrize("batch", [900, 40000])   # one block / many blocks (last-block election)
+def test_group_adam_dev_advances_beta_powers_in_the_same_launch(batch):
+  # AdamOptimizer._finish folded into the apply: powers advance exactly once per launch
+  dim = 16
+  var = Pair(dim)
+  slot = Pair(3 * dim, init=0.0)
+  lr, b1, b2, eps = 0.02, 0.9, 0.999, 1e-8
+  hp = torch.tensor([lr, b1, b2, b1, b2, eps, 1e-5, 1e-5, 0.0], dtype=torch.float32, device=DEV)
+  b1p, b2p = np.float32(b1), np.float32(b2)
+  for ids, u, g in _steps(4, batch, batch, dim, seed=21):
+    var.gather_or_insert(ids)
+    ops.kv_variable_group_sparse_apply_adam_v4_dev(var.gpu, slot.gpu, t(g), t(u), hp,
+                                                   advance_powers=True)
+    ob.apply_group_adam_v4(var.cpu, slot.cpu, u, g, lr, float(b1p), float(b2p), b1, b2, eps,
+                           1e-5, 1e-5, 0.0, today=TODAY)
+    b1p, b2p = b1p * np.float32(b1), b2p * np.float32(b2)
+    got = hp.cpu().numpy()
+    assert got[1] == b1p and got[2] == b2p
+  # an empty apply still counts as a step
+  ops.kv_variable_group_sparse_apply_adam_v4_dev(var.gpu, slot.gpu, torch.empty(0, dim, device=DEV),
+                                                 torch.empty(0, dtype=torch.int64, device=DEV), hp,
+                                                 advance_powers=True)
+  got = hp.cpu().numpy()
+  assert got[1] == b1p * np.float32(b1) and got[2] == b2p * np.float32(b2)
+  var.check_state(rtol=RTOL, atol=ATOL)
+  slot.check_state(rtol=RTOL, atol=ATOL)
+
+
 def test_apply_reads_count_from_device():
   dim = 16
   var = Pair(dim)

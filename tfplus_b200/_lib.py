@@ -48,6 +48,8 @@ SIGNATURES = {
     "kv_apply_group_adam_v4_dev": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_apply_sparse_group_ftrl_dev": [vp, vp, vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_apply_adam_dev": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
+    "kv_apply_group_adam_v4_dev_advance": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
+    "kv_apply_adam_dev_advance": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_workspace_create": [C.POINTER(vp)],
     "kv_workspace_destroy": [vp],
     "kv_unique": [vp, vp, i64, vp, vp, vp, vp, vp],

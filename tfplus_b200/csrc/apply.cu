@@ -270,10 +270,11 @@ __device__ __forceinline__ void row_update(const ApplyParams& p, int dim, int tp
 //  phase 3, lanes < kpw: publish flags (under-threshold, blacklist) and finish the atomics.
 // kpw is chosen on the host so that one wave of warps covers the whole launch.
 template <int VEC, int CPL, int KIND, int UNR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CPL == 1 ? 5 : 1)
 apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restrict__ ids,
              const float* __restrict__ grad, long long n, const int* __restrict__ d_n,
-             ApplyParams p, const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw) {
+             ApplyParams p, const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw,
+             float* d_adv) {
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p.update_slots);
   constexpr int PARTS = Kind<KIND>::PARTS;
   constexpr bool TWO = Kind<KIND>::TWO;
@@ -488,12 +489,34 @@ apply_kernel(TableView var, TableView sa, TableView sb, const long long* __restr
     r[0] = t0; r[1] = gtime_a(); r[2] = t2; r[3] = t1;
   }
 #endif
+  // AdamOptimizer._finish (beta1_power *= beta1, beta2_power *= beta2; inherited by
+  // python/training/group_adam.py) folded into this launch: every block read the powers when
+  // it started, so the block that finishes last may advance them for the next step.
+  if ((KIND == K_GROUP_ADAM || KIND == K_ADAM) && d_adv != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned done = atomicAdd(&var.ctr->apply_done, 1u);
+      if (done == gridDim.x - 1) {
+        constexpr int P = KIND == K_GROUP_ADAM ? 1 : 4;   // index of beta1_power in hp
+        constexpr int Bt = KIND == K_GROUP_ADAM ? 3 : 1;  // index of beta1 in hp
+        d_adv[P] = d_adv[P] * d_adv[Bt];
+        d_adv[P + 1] = d_adv[P + 1] * d_adv[Bt + 1];
+        var.ctr->apply_done = 0;
+      }
+    }
+  }
+}
+
+__global__ void advance_powers_kernel(float* hp, int p, int b) {
+  hp[p] = hp[p] * hp[b];
+  hp[p + 1] = hp[p + 1] * hp[b + 1];
 }
 
 template <int VEC, int CPL, int KIND>
 int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
                  int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
-                 uint16_t today, cudaStream_t st, int tpr) {
+                 uint16_t today, cudaStream_t st, int tpr, float* d_adv) {
   static const int kpw_env = getenv("KVHBM_APPLY_KPW") ? atoi(getenv("KVHBM_APPLY_KPW")) : 0;
   static const int unr_env = getenv("KVHBM_APPLY_UNR") ? atoi(getenv("KVHBM_APPLY_UNR")) : 0;
   // ids per warp: the smallest power of two that keeps the launch within ~1.5 waves of warps
@@ -512,7 +535,7 @@ int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const flo
   const bool two = (CPL == 1) && unr_env == 2;
 #define KV_A(U) apply_kernel<VEC, CPL, KIND, U><<<blocks, 128, 0, st>>>(                          \
       var->view(), sa->view(), vb, reinterpret_cast<const long long*>(ids), grad, n, d_n, p,     \
-      d_hp, today, tpr, kpw)
+      d_hp, today, tpr, kpw, d_adv)
   if (two) KV_A(2); else KV_A(1);
 #undef KV_A
   KV_LAUNCHED();
@@ -522,8 +545,15 @@ int launch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const flo
 template <int KIND>
 int dispatch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
                    int64_t n, const int32_t* d_n, const ApplyParams& p, const float* d_hp,
-                   uint16_t today, cudaStream_t st) {
-  if (n <= 0) return 0;
+                   uint16_t today, cudaStream_t st, float* d_adv) {
+  if (n <= 0) {
+    if (d_adv) {  // nothing to update, but the step still counts
+      advance_powers_kernel<<<1, 1, 0, st>>>(d_adv, KIND == K_GROUP_ADAM ? 1 : 4,
+                                             KIND == K_GROUP_ADAM ? 3 : 1);
+      KV_LAUNCHED();
+    }
+    return 0;
+  }
   KV_TRY(var->ensure(n, st));
   KV_TRY(sa->ensure(n, st));
   if (sb) KV_TRY(sb->ensure(n, st));
@@ -532,7 +562,7 @@ int dispatch_apply(Table* var, Table* sa, Table* sb, const int64_t* ids, const f
     return fail(3, "fused apply: embedding dim " + std::to_string(var->dim) +
                        " not supported (max 512 when a multiple of 4, else 128)");
   const int cpl = g.cpl == 3 ? 4 : g.cpl;
-#define CALL(V, C) launch_apply<V, C, KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st, g.tpr)
+#define CALL(V, C) launch_apply<V, C, KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st, g.tpr, d_adv)
   if (g.vec == 4) {
     if (cpl == 1) return CALL(4, 1);
     if (cpl == 2) return CALL(4, 2);
@@ -558,11 +588,12 @@ int check_initialized(const Table* t, const char* what) {
 template <int KIND>
 static int apply_common(Table* var, Table* sa, Table* sb, const int64_t* ids, const float* grad,
                         int64_t n, const int32_t* d_n, const float* hp, const float* d_hp,
-                        int update_slots, uint16_t today, cudaStream_t st) {
+                        int update_slots, uint16_t today, cudaStream_t st,
+                        float* d_adv = nullptr) {
   ApplyParams p{};
   if (d_hp == nullptr) p = derive_params<KIND>(hp, var->dim, update_slots);
   p.update_slots = update_slots;
-  return dispatch_apply<KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st);
+  return dispatch_apply<KIND>(var, sa, sb, ids, grad, n, d_n, p, d_hp, today, st, d_adv);
 }
 
 int do_apply_adagrad(Table* var, Table* accum, const int64_t* ids, const float* grad, int64_t n,
@@ -577,7 +608,7 @@ int do_apply_adagrad(Table* var, Table* accum, const int64_t* ids, const float* 
 
 int do_apply_group_adam_v4(Table* var, Table* mvl, const int64_t* ids, const float* grad,
                            int64_t n, const int32_t* d_n, const float* hp, const float* d_hp,
-                           uint16_t today, cudaStream_t st) {
+                           uint16_t today, cudaStream_t st, float* d_adv) {
   // argument checks of training_ops.cc:7001-7103
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(mvl, "m_v_linear"));
@@ -589,7 +620,8 @@ int do_apply_group_adam_v4(Table* var, Table* mvl, const int64_t* ids, const flo
   }
   if (mvl->dim != 3 * var->dim)
     return fail(1, "kv_variable and linear do not have the same shape");
-  return apply_common<K_GROUP_ADAM>(var, mvl, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st);
+  return apply_common<K_GROUP_ADAM>(var, mvl, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st,
+                                    d_adv);
 }
 
 int do_apply_sparse_group_ftrl(Table* var, Table* accum, Table* linear, const int64_t* ids,
@@ -615,11 +647,11 @@ int do_apply_sparse_group_ftrl(Table* var, Table* accum, Table* linear, const in
 
 int do_apply_adam(Table* var, Table* mv, const int64_t* ids, const float* grad, int64_t n,
                   const int32_t* d_n, const float* hp, const float* d_hp, uint16_t today,
-                  cudaStream_t st) {
+                  cudaStream_t st, float* d_adv) {
   KV_TRY(check_initialized(var, "var"));
   KV_TRY(check_initialized(mv, "m_v"));
   if (mv->dim != 2 * var->dim) return fail(1, "m_v slot must have dim 2 * dim(var)");
-  return apply_common<K_ADAM>(var, mv, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st);
+  return apply_common<K_ADAM>(var, mv, nullptr, ids, grad, n, d_n, hp, d_hp, 1, today, st, d_adv);
 }
 
 }  // namespace kvhbm

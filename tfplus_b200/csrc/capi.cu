@@ -27,12 +27,14 @@ int do_permute_rows(bool scatter, const float*, const int32_t*, int64_t, int, fl
 int do_apply_adagrad(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
                      const float* hp, const float* d_hp, int, uint16_t, cudaStream_t);
 int do_apply_group_adam_v4(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
-                           const float* hp, const float* d_hp, uint16_t, cudaStream_t);
+                           const float* hp, const float* d_hp, uint16_t, cudaStream_t,
+                           float* d_adv = nullptr);
 int do_apply_sparse_group_ftrl(Table*, Table*, Table*, const int64_t*, const float*, int64_t,
                                const int32_t*, const float* hp, const float* d_hp, uint16_t,
                                cudaStream_t);
 int do_apply_adam(Table*, Table*, const int64_t*, const float*, int64_t, const int32_t*,
-                  const float* hp, const float* d_hp, uint16_t, cudaStream_t);
+                  const float* hp, const float* d_hp, uint16_t, cudaStream_t,
+                  float* d_adv = nullptr);
 
 int do_unique(Workspace*, const int64_t*, int64_t, int64_t*, int32_t*, int32_t*, int32_t*,
               cudaStream_t);
@@ -302,6 +304,15 @@ int kv_apply_group_adam_v4_dev(kv_table* var, kv_table* mvl, const int64_t* d_id
   return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today,
                                 S(stream));
 }
+int kv_apply_group_adam_v4_dev_advance(kv_table* var, kv_table* mvl, const int64_t* d_ids,
+                                       const float* d_grad, int64_t n, const int32_t* d_n,
+                                       float* d_hp, uint16_t today, kv_stream stream) {
+  MultiGuard g(var, mvl, nullptr);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today,
+                                S(stream), d_hp);
+}
 int kv_apply_sparse_group_ftrl_dev(kv_table* var, kv_table* accum, kv_table* linear,
                                    const int64_t* d_ids, const float* d_grad, int64_t n,
                                    const int32_t* d_n, const float* d_hp, uint16_t today,
@@ -319,6 +330,16 @@ int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids, const 
   if (g.rc) return g.rc;
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream));
+}
+
+int kv_apply_adam_dev_advance(kv_table* var, kv_table* m_v, const int64_t* d_ids,
+                              const float* d_grad, int64_t n, const int32_t* d_n, float* d_hp,
+                              uint16_t today, kv_stream stream) {
+  MultiGuard g(var, m_v, nullptr);
+  if (g.rc) return g.rc;
+  KV_NEED(d_hp != nullptr, "d_hp is null");
+  return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream),
+                       d_hp);
 }
 
 int kv_workspace_create(kv_workspace** out) {

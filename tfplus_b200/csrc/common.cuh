@@ -45,6 +45,8 @@ struct Counters {
   long long free_top;            // entries on the free-row stack
   unsigned long long tombstones;
   unsigned long long scratch[4];  // per-call reduction results (size, sum_freq, export counts)
+  unsigned int apply_done;        // blocks of the running apply launch that have finished
+  unsigned int pad_;
 };
 
 // What a kernel needs to know about one table; passed by value.

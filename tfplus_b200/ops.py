@@ -521,14 +521,20 @@ def kv_variable_sparse_apply_adagrad_dev(var, accum, hparams, grad, indices, upd
 
 
 def kv_variable_group_sparse_apply_adam_v4_dev(var, m_v_linear, grad, indices, hparams,
-                                               num_indices=None):
+                                               num_indices=None, advance_powers=False):
   """KvVariableGroupSparseApplyAdamV4 with hparams = [lr, beta1_power, beta2_power, beta1,
-  beta2, epsilon, l1, l2, l21] in device memory (graph-capturable)."""
+  beta2, epsilon, l1, l2, l21] in device memory (graph-capturable).  advance_powers: the same
+  launch then multiplies the two powers by their betas in `hparams` (AdamOptimizer._finish)."""
   ids, g, dn = _apply_args(var, grad, indices, num_indices)
   hp = _hp(var, hparams, 9)
-  check(var._lib.kv_apply_group_adam_v4_dev(var._live(), m_v_linear._live(), ids.data_ptr(),
-                                            g.data_ptr(), ids.numel(), _ptr(dn), hp.data_ptr(),
-                                            today(), var.stream))
+  if advance_powers:
+    if not hparams.is_contiguous():
+      raise ValueError("InvalidArgument: advance_powers needs contiguous hparams")
+    fn = var._lib.kv_apply_group_adam_v4_dev_advance
+  else:
+    fn = var._lib.kv_apply_group_adam_v4_dev
+  check(fn(var._live(), m_v_linear._live(), ids.data_ptr(), g.data_ptr(), ids.numel(), _ptr(dn),
+           hp.data_ptr(), today(), var.stream))
 
 
 def kv_variable_sparse_group_sparse_apply_ftrl_v2_dev(var, accum, linear, grad, indices, hparams,
@@ -542,12 +548,17 @@ def kv_variable_sparse_group_sparse_apply_ftrl_v2_dev(var, accum, linear, grad, 
                                                 _ptr(dn), hp.data_ptr(), today(), var.stream))
 
 
-def kv_variable_sparse_apply_adam_dev(var, m_v, grad, indices, hparams, num_indices=None):
-  """Fused tfplus-Adam with hparams = [lr, beta1, beta2, epsilon, beta1_power, beta2_power]."""
+def kv_variable_sparse_apply_adam_dev(var, m_v, grad, indices, hparams, num_indices=None,
+                                      advance_powers=False):
+  """Fused tfplus-Adam with hparams = [lr, beta1, beta2, epsilon, beta1_power, beta2_power];
+  advance_powers as in kv_variable_group_sparse_apply_adam_v4_dev."""
   ids, g, dn = _apply_args(var, grad, indices, num_indices)
   hp = _hp(var, hparams, 6)
-  check(var._lib.kv_apply_adam_dev(var._live(), m_v._live(), ids.data_ptr(), g.data_ptr(),
-                                   ids.numel(), _ptr(dn), hp.data_ptr(), today(), var.stream))
+  if advance_powers and not hparams.is_contiguous():
+    raise ValueError("InvalidArgument: advance_powers needs contiguous hparams")
+  fn = var._lib.kv_apply_adam_dev_advance if advance_powers else var._lib.kv_apply_adam_dev
+  check(fn(var._live(), m_v._live(), ids.data_ptr(), g.data_ptr(), ids.numel(), _ptr(dn),
+           hp.data_ptr(), today(), var.stream))
 
 
 # ---------------------------------------------------------------------------

@@ -244,8 +244,8 @@ class PaddedShardedStep:
     ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum,
                              accumulate=True)
     ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
-                                                   self.hpt, num_indices=self.o_num)
-    self.hpt[1:3].mul_(self.betas)
+                                                   self.hpt, num_indices=self.o_num,
+                                                   advance_powers=True)
     return out
 
   def overflowed(self):
@@ -363,8 +363,8 @@ class PeerShardedStep(PaddedShardedStep):
     ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
                              accumulate=True)
     ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
-                                                   self.hpt, num_indices=self.o_num)
-    self.hpt[1:3].mul_(self.betas)
+                                                   self.hpt, num_indices=self.o_num,
+                                                   advance_powers=True)
     with t.cuda.stream(s1):
       s1.wait_event(ev_b)
       ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, out)
