@@ -296,6 +296,19 @@ int kv_route_ids_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_o
                       const int32_t* d_n, int num_shards, int mode, int capacity,
                       int64_t* const* d_seg_ids, int32_t* const* d_seg_occ, int32_t* d_perm,
                       int32_t* d_counts, int32_t* d_overflow, kv_stream stream);
+/* kv_unique and kv_route_ids_peer in the same three launches: the kernel that ranks the first
+ * occurrences also gives each distinct id a position in its owner's row and stores {id,
+ * occurrence count} there.  d_perm[r] is the padded position of unique id r (or -1 and
+ * *d_overflow = 1).  The rows must have been padded, and d_shard_counts zeroed, by
+ * kv_route_fill_peer since the previous call (it can run any time after the owners have read
+ * the previous step's ids, e.g. under the rest of the step). */
+int kv_unique_route_peer(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq,
+                         int32_t* d_idx, int32_t* d_counts, int32_t* d_num_unique,
+                         int num_shards, int mode, int capacity, int64_t* const* d_seg_ids,
+                         int32_t* const* d_seg_occ, int32_t* d_perm, int32_t* d_shard_counts,
+                         int32_t* d_overflow, kv_stream stream);
+int kv_route_fill_peer(int num_shards, int capacity, int64_t* const* d_seg_ids,
+                       int32_t* const* d_seg_occ, int32_t* d_shard_counts, kv_stream stream);
 /* kv_gather_or_insert whose row r is written to d_seg_rows[r / capacity] + (r % capacity) * dim;
  * rows of padding ids are not written at all. */
 int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,

@@ -178,6 +178,97 @@ def test_pad_ids_are_ignored_and_row_helpers():
   np.testing.assert_array_equal(dst.cpu().numpy(), want)
 
 
+def _segments(buf, G):
+  """Device array of G pointers to the G equal row-blocks of `buf` (what a peer table is,
+  with every "peer" living on this GPU)."""
+  step = buf.numel() // G * buf.element_size()
+  return torch.tensor([buf.data_ptr() + g * step for g in range(G)], dtype=torch.int64, device=DEV)
+
+
+def test_peer_variants_equal_the_local_ones_on_one_gpu():
+  # the _peer entry points only change WHERE a row is stored: same kernels, segment pointers
+  rng = np.random.default_rng(17)
+  G, cap, D = 4, 1024, 16
+  ids = np.unique(rng.integers(-2**40, 2**40, size=3000).astype(np.int64))
+  occ = rng.integers(1, 9, size=ids.size).astype(np.int32)
+  num = torch.tensor([ids.size - 50], dtype=torch.int32, device=DEV)
+  ref = ops.route_ids(t(ids), t(occ), G, cap, "hash", num_ids=num)
+  ids_in = torch.zeros(G * cap, dtype=torch.int64, device=DEV)
+  occ_in = torch.full((G * cap,), -1, dtype=torch.int32, device=DEV)
+  out = {"perm": torch.empty(ids.size, dtype=torch.int32, device=DEV),
+         "counts": torch.empty(G, dtype=torch.int32, device=DEV),
+         "overflow": torch.zeros(1, dtype=torch.int32, device=DEV)}
+  ops.route_ids_peer(t(ids), t(occ), G, cap, "hash", num, _segments(ids_in, G),
+                     _segments(occ_in, G), out)
+  np.testing.assert_array_equal(out["counts"].cpu().numpy(), ref["counts"].cpu().numpy())
+  got_ids, got_occ = ids_in.cpu().numpy().reshape(G, cap), occ_in.cpu().numpy().reshape(G, cap)
+  want_ids = ref["send_ids"].cpu().numpy().reshape(G, cap)
+  want_occ = ref["send_occ"].cpu().numpy().reshape(G, cap)
+  for g in range(G):      # order inside a shard row is launch-dependent: compare as multisets
+    assert sorted(zip(got_ids[g].tolist(), got_occ[g].tolist())) == \
+           sorted(zip(want_ids[g].tolist(), want_occ[g].tolist()))
+  perm = out["perm"].cpu().numpy()[:ids.size - 50]
+  np.testing.assert_array_equal(got_ids.reshape(-1)[perm], ids[:ids.size - 50])
+  assert int(out["overflow"].item()) == 0
+
+  # dedup + route fused: same shard rows as unique followed by route
+  raw = rng.choice(ids[:2000], size=9000).astype(np.int64)
+  B = raw.size
+  uq = {k: torch.empty(B, dtype=d, device=DEV) for k, d in
+        [("uniq", torch.int64), ("idx", torch.int32), ("cnt", torch.int32)]}
+  num2 = torch.zeros(1, dtype=torch.int32, device=DEV)
+  ids2 = torch.zeros(G * cap, dtype=torch.int64, device=DEV)
+  occ2 = torch.full((G * cap,), -1, dtype=torch.int32, device=DEV)
+  out2 = {"perm": torch.full((B,), -7, dtype=torch.int32, device=DEV),
+          "counts": torch.full((G,), 99, dtype=torch.int32, device=DEV),
+          "overflow": torch.zeros(1, dtype=torch.int32, device=DEV)}
+  ops.route_fill_peer(G, cap, _segments(ids2, G), _segments(occ2, G), out2["counts"])
+  assert (ids2 == PAD).all() and (occ2 == 0).all() and (out2["counts"] == 0).all()
+  ops.unique_route_peer(t(raw), uq["uniq"], uq["idx"], uq["cnt"], num2, G, cap, "hash",
+                        _segments(ids2, G), _segments(occ2, G), out2)
+  u_ref, idx_ref = ob.unique(raw)
+  n_u = int(num2.item())
+  assert n_u == u_ref.size
+  np.testing.assert_array_equal(uq["uniq"].cpu().numpy()[:n_u], u_ref)
+  np.testing.assert_array_equal(uq["idx"].cpu().numpy(), idx_ref)
+  c_ref = np.bincount(idx_ref, minlength=n_u)
+  np.testing.assert_array_equal(uq["cnt"].cpu().numpy()[:n_u], c_ref)
+  own = owner_of(u_ref, G)
+  np.testing.assert_array_equal(out2["counts"].cpu().numpy(), np.bincount(own, minlength=G))
+  perm2 = out2["perm"].cpu().numpy()[:n_u]
+  np.testing.assert_array_equal(perm2 // cap, own)
+  np.testing.assert_array_equal(ids2.cpu().numpy()[perm2], u_ref)
+  np.testing.assert_array_equal(occ2.cpu().numpy()[perm2], c_ref)
+  assert (ids2 != PAD).sum().item() == n_u and int(out2["overflow"].item()) == 0
+
+  # owner lookup into segments == plain lookup; padding rows are left untouched
+  p, q = Pair(D), Pair(D)
+  recv = ids_in.clone()
+  counts = t(occ_in.clamp(min=0).cpu().numpy())
+  rows_seg = torch.full((G * cap, D), 7.0, device=DEV)
+  ops.kv_variable_gather_or_insert_peer(p.gpu, recv, counts, _segments(rows_seg, G), cap)
+  rows_ref = ops.kv_variable_gather_or_insert_with_counts(q.gpu, recv, counts)
+  pad = (recv == PAD).cpu().numpy()
+  np.testing.assert_array_equal(rows_seg.cpu().numpy()[~pad], rows_ref.cpu().numpy()[~pad])
+  assert (rows_seg.cpu().numpy()[pad] == 7.0).all()
+  p.cpu.gather_or_insert(recv.cpu().numpy()[~pad], counts.cpu().numpy()[~pad], today=TODAY)
+  p.check_state()
+
+  # gradient rows into segments == scatter_rows_n
+  src = torch.randn(ids.size, D, device=DEV)
+  a, b = torch.zeros(G * cap, D, device=DEV), torch.zeros(G * cap, D, device=DEV)
+  ops.scatter_rows_n(src, out["perm"], ids.size, num, a)
+  ops.scatter_rows_n_peer(src, out["perm"], ids.size, num, _segments(b, G), cap)
+  np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+
+  # a one-GPU "world" needs no barrier; bad arguments are refused
+  flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+  state = torch.zeros(2, dtype=torch.int32, device=DEV)
+  ops.peer_barrier(_segments(flags, 1), flags, state, 0, 1)
+  with pytest.raises(Exception):
+    ops.peer_barrier(_segments(flags, 1), flags, state, 3, 2)
+
+
 def _padded_worker(rank, world, port, q, use_graph, exchange="nccl"):
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
   torch.cuda.set_device(rank)

@@ -69,6 +69,8 @@ SIGNATURES = {
     "kv_permute_rows": [vp, vp, i64, i32, vp, vp],
     "kv_scatter_rows": [vp, vp, i64, i32, vp, vp],
     "kv_route_ids_peer": [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
+    "kv_unique_route_peer": [vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
+    "kv_route_fill_peer": [i32, i32, vp, vp, vp, vp],
     "kv_gather_or_insert_peer": [vp, vp, vp, i64, vp, i64, u16, vp],
     "kv_scatter_rows_n_peer": [vp, vp, i64, vp, i32, vp, i64, vp],
     "kv_peer_barrier": [vp, vp, vp, i32, i32, i64, vp],

@@ -51,6 +51,10 @@ int do_gather_segments(Table*, const int64_t*, const int32_t*, int64_t, float* c
                        uint16_t, cudaStream_t);
 int do_peer_barrier(uint32_t* const*, uint32_t*, uint32_t*, int, int, int64_t, cudaStream_t);
 int do_unzip_pairs(const int64_t*, int64_t, int64_t*, int32_t*, cudaStream_t);
+int do_unique_route(Workspace*, const int64_t*, int64_t, int64_t*, int32_t*, int32_t*, int32_t*,
+                    int, int, int, int64_t* const*, int32_t* const*, int32_t*, int32_t*,
+                    int32_t*, cudaStream_t);
+int do_route_fill(int, int, int64_t* const*, int32_t* const*, int32_t*, cudaStream_t);
 int do_expand_rows(const float*, const int32_t*, const int32_t*, int64_t, int, float*, cudaStream_t);
 int do_scatter_rows_n(const float*, const int32_t*, int64_t, const int32_t*, int, float*,
                       float* const*, int64_t, cudaStream_t);
@@ -450,6 +454,23 @@ int kv_route_ids_peer(kv_workspace* ws, const int64_t* d_ids, const int32_t* d_o
           "route_ids_peer: bad arguments");
   return do_route_ids(ws->w, d_ids, d_occ, n, d_n, num_shards, mode, capacity, nullptr, nullptr,
                       d_perm, d_counts, d_overflow, /*pairs=*/0, d_seg_ids, d_seg_occ, S(stream));
+}
+int kv_unique_route_peer(kv_workspace* ws, const int64_t* d_ids, int64_t n, int64_t* d_uniq,
+                         int32_t* d_idx, int32_t* d_counts, int32_t* d_num_unique,
+                         int num_shards, int mode, int capacity, int64_t* const* d_seg_ids,
+                         int32_t* const* d_seg_occ, int32_t* d_perm, int32_t* d_shard_counts,
+                         int32_t* d_overflow, kv_stream stream) {
+  KV_NEED(ws && d_num_unique && d_seg_ids && d_seg_occ && d_shard_counts && d_overflow &&
+              (n == 0 || (d_ids && d_uniq && d_idx && d_perm)),
+          "unique_route_peer: bad arguments");
+  return do_unique_route(ws->w, d_ids, n, d_uniq, d_idx, d_counts, d_num_unique, num_shards, mode,
+                         capacity, d_seg_ids, d_seg_occ, d_perm, d_shard_counts, d_overflow,
+                         S(stream));
+}
+int kv_route_fill_peer(int num_shards, int capacity, int64_t* const* d_seg_ids,
+                       int32_t* const* d_seg_occ, int32_t* d_shard_counts, kv_stream stream) {
+  KV_NEED(d_seg_ids && d_seg_occ && d_shard_counts, "route_fill_peer: bad arguments");
+  return do_route_fill(num_shards, capacity, d_seg_ids, d_seg_occ, d_shard_counts, S(stream));
 }
 int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
                              int64_t n, float* const* d_seg_rows, int64_t capacity,

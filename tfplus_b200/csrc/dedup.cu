@@ -38,6 +38,28 @@ namespace {
 
 constexpr int UB = 1024;  // ids per block in the scan kernels (256 threads x 4)
 
+constexpr int MAX_SHARDS = 256;
+
+__device__ __forceinline__ int owner_of(long long id, int num_shards, int mode) {
+  if (mode == 1) {  // google_floor_mod, kernels/utility.h:95-101
+    long long m = id % num_shards;
+    return (int)(m < 0 ? m + num_shards : m);
+  }
+  // low bits of the hash; the slot index uses the high bits (common.cuh)
+  return (int)(mix64((unsigned long long)id ^ 0x5446534dULL) % (unsigned long long)num_shards);
+}
+
+// Where the rank kernel sends each distinct id when dedup and routing are fused
+// (kv_unique_route_peer): shard g's row is dst_ids[g] / dst_occ[g], normally peer g's inbox.
+struct RouteOut {
+  long long* const* dst_ids;
+  int* const* dst_occ;
+  int* perm;          // [n]: padded position g * cap + r of unique id r, or -1 (overflow)
+  int* shard_counts;  // [num_shards], zeroed by kv_route_fill_peer
+  int* overflow;
+  int num_shards, mode, cap;
+};
+
 struct __align__(16) USlot {
   long long key;
   int first;  // smallest position holding this key; once ranked, ~rank (negative)
@@ -124,11 +146,16 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
 // counts its first occurrences, publishes the count, and obtains the number of first
 // occurrences before it by decoupled look-back over the earlier blocks' status words
 // (flag 1 = block aggregate, flag 2 = inclusive prefix; value in the low 32 bits).
+//
+// ROUTE: the same launch is the id exchange of the sharded step — a first occurrence is also
+// given a position in its owner's row (shared histogram, one global add per (block, shard))
+// and stored, with its occurrence count, straight into that row (peer memory).
+template <bool ROUTE>
 __global__ void __launch_bounds__(256)
 unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
                    const long long* __restrict__ ids, long long n,
                    long long* __restrict__ uniq, int* __restrict__ counts,
-                   int* __restrict__ num_unique) {
+                   int* __restrict__ num_unique, RouteOut ro) {
   __shared__ int warp_tot[8];
   __shared__ int block_prefix;
   const int which = sc.sel[0] & 1;
@@ -186,15 +213,52 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
   }
   __syncthreads();
   int r = block_prefix + woff + incl - c;
+  long long key[4];
+  int cnt[4], rk[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (f[k]) {
       // the other occurrences only test first == their own position: ~r is negative, so
       // overwriting first with the rank cannot turn any of them into a first occurrence
-      uniq[r] = ids[i0 + k];
-      if (counts) counts[r] = tab[s[k]].count;
+      key[k] = ids[i0 + k];
+      uniq[r] = key[k];
+      cnt[k] = (counts || ROUTE) ? tab[s[k]].count : 1;
+      if (counts) counts[r] = cnt[k];
       tab[s[k]].first = ~r;
+      rk[k] = r;
       ++r;
+    }
+  }
+  if (ROUTE) {
+    __shared__ int hist[MAX_SHARDS];
+    __shared__ int basepos[MAX_SHARDS];
+    for (int g = threadIdx.x; g < ro.num_shards; g += blockDim.x) hist[g] = 0;
+    __syncthreads();
+    int own[4], lr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (f[k]) {
+        own[k] = owner_of(key[k], ro.num_shards, ro.mode);
+        lr[k] = atomicAdd(&hist[own[k]], 1);
+      }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < ro.num_shards; g += blockDim.x)
+      basepos[g] = hist[g] ? atomicAdd(&ro.shard_counts[g], hist[g]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (f[k]) {
+        const int pos = basepos[own[k]] + lr[k];
+        if (pos < ro.cap) {
+          ro.dst_ids[own[k]][pos] = key[k];
+          ro.dst_occ[own[k]][pos] = cnt[k];
+          ro.perm[rk[k]] = own[k] * ro.cap + pos;
+        } else {
+          ro.perm[rk[k]] = -1;  // does not fit: reported, the caller falls back to the exact path
+          atomicExch(ro.overflow, 1);
+        }
+      }
     }
   }
 }
@@ -347,17 +411,6 @@ segment_sum_kernel(const float* __restrict__ data, const int* __restrict__ idx, 
 }
 
 // ---- id routing for key-hash sharding -----------------------------------------
-constexpr int MAX_SHARDS = 256;
-
-__device__ __forceinline__ int owner_of(long long id, int num_shards, int mode) {
-  if (mode == 1) {  // google_floor_mod, kernels/utility.h:95-101
-    long long m = id % num_shards;
-    return (int)(m < 0 ? m + num_shards : m);
-  }
-  // low bits of the hash; the slot index uses the high bits (common.cuh)
-  return (int)(mix64((unsigned long long)id ^ 0x5446534dULL) % (unsigned long long)num_shards);
-}
-
 __global__ void __launch_bounds__(256)
 partition_count_kernel(const long long* __restrict__ ids, long long n, const int* d_n,
                        int num_shards, int mode, int* __restrict__ shard_counts) {
@@ -530,8 +583,8 @@ size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 static bool ws_wiped(const Workspace* ws) { return ws->wiped_buf == ws->ubuf; }
 static void ws_mark_wiped(Workspace* ws) { ws->wiped_buf = ws->ubuf; }
 
-int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
-              int32_t* counts, int32_t* num_unique, cudaStream_t st) {
+int do_unique_impl(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
+                   int32_t* counts, int32_t* num_unique, const RouteOut* route, cudaStream_t st) {
   if (n < 0 || n > (1LL << 30)) return fail(1, "unique: n out of range");
   if (n == 0) {
     KV_CUDA(cudaMemsetAsync(num_unique, 0, sizeof(int32_t), st));
@@ -581,14 +634,59 @@ int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32
     KV_LAUNCHED();
     ws_mark_wiped(ws);
   }
-  if (counts) unique_insert_kernel<true><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
+  if (counts || route) unique_insert_kernel<true><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
   else unique_insert_kernel<false><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
   KV_LAUNCHED();
-  unique_rank_kernel<<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
-                                         counts, num_unique);
+  if (route)
+    unique_rank_kernel<true><<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
+                                                 counts, num_unique, *route);
+  else
+    unique_rank_kernel<false><<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
+                                                  counts, num_unique, RouteOut{});
   KV_LAUNCHED();
   const long long span = n > (long long)sc.cap ? n : (long long)sc.cap;
   unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx);
+  KV_LAUNCHED();
+  return 0;
+}
+
+int do_unique(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
+              int32_t* counts, int32_t* num_unique, cudaStream_t st) {
+  return do_unique_impl(ws, ids, n, uniq, idx, counts, num_unique, nullptr, st);
+}
+
+// kv_unique + kv_route_ids_peer in the same three launches (the rank kernel routes).
+int do_unique_route(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
+                    int32_t* counts, int32_t* num_unique, int num_shards, int mode, int cap,
+                    int64_t* const* dst_ids, int32_t* const* dst_occ, int32_t* perm,
+                    int32_t* shard_counts, int32_t* overflow, cudaStream_t st) {
+  if (num_shards < 1 || num_shards > MAX_SHARDS)
+    return fail(1, "unique_route: num_shards must be in [1, 256]");
+  if (cap < 1) return fail(1, "unique_route: capacity must be positive");
+  RouteOut ro;
+  ro.dst_ids = reinterpret_cast<long long* const*>(dst_ids);
+  ro.dst_occ = dst_occ;
+  ro.perm = perm;
+  ro.shard_counts = shard_counts;
+  ro.overflow = overflow;
+  ro.num_shards = num_shards;
+  ro.mode = mode;
+  ro.cap = cap;
+  return do_unique_impl(ws, ids, n, uniq, idx, counts, num_unique, &ro, st);
+}
+
+// Padding + zeroed shard counters for the next kv_unique_route_peer / kv_route_ids_peer.
+int do_route_fill(int num_shards, int cap, int64_t* const* dst_ids, int32_t* const* dst_occ,
+                  int32_t* shard_counts, cudaStream_t st) {
+  if (num_shards < 1 || num_shards > MAX_SHARDS)
+    return fail(1, "route_fill: num_shards must be in [1, 256]");
+  if (cap < 1) return fail(1, "route_fill: capacity must be positive");
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  const long long total = (long long)num_shards * cap;
+  route_fill_kernel<<<blocks_for(total, 256, dev), 256, 0, st>>>(
+      nullptr, nullptr, total, shard_counts, num_shards, 0,
+      reinterpret_cast<long long* const*>(dst_ids), dst_occ, cap);
   KV_LAUNCHED();
   return 0;
 }

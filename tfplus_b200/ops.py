@@ -712,6 +712,29 @@ def route_ids_peer(ids, occ, num_shards, capacity, mode, num_ids, seg_ids, seg_o
   return out
 
 
+def unique_route_peer(ids, uniq, idx, counts, num, num_shards, capacity, mode, seg_ids, seg_occ,
+                      out):
+  """kv_unique_route_peer: unique_into + route_ids_peer in the same launches;
+  out = dict(perm, counts (per shard, zeroed by route_fill_peer), overflow)."""
+  ws = Workspace.get(ids.device)
+  with torch.cuda.device(ids.device):
+    check(_lib.load().kv_unique_route_peer(ws.ptr, ids.data_ptr(), ids.numel(), uniq.data_ptr(),
+                                           idx.data_ptr(), _ptr(counts), num.data_ptr(),
+                                           num_shards, 1 if mode == "mod" else 0, capacity,
+                                           seg_ids.data_ptr(), seg_occ.data_ptr(),
+                                           out["perm"].data_ptr(), out["counts"].data_ptr(),
+                                           out["overflow"].data_ptr(), _stream(ids.device)))
+  return out
+
+
+def route_fill_peer(num_shards, capacity, seg_ids, seg_occ, shard_counts):
+  """kv_route_fill_peer: pad the owners' rows and zero the shard counters for the next step."""
+  with torch.cuda.device(shard_counts.device):
+    check(_lib.load().kv_route_fill_peer(num_shards, capacity, seg_ids.data_ptr(),
+                                         seg_occ.data_ptr(), shard_counts.data_ptr(),
+                                         _stream(shard_counts.device)))
+
+
 def kv_variable_gather_or_insert_peer(table_handle, indices, counts, seg, capacity):
   """KvVariableGatherOrInsertWithCounts whose row r lands in seg[r // capacity][r % capacity]."""
   h = table_handle

@@ -319,7 +319,16 @@ class PeerShardedStep(PaddedShardedStep):
     self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
     self.side2 = t.cuda.Stream(device=self.dev)
+    if os.environ.get("KVHBM_PEER_PRIO", "0") == "1":   # owner dedup is the critical branch
+      self.side = t.cuda.Stream(device=self.dev, priority=-1)
     self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
+    # dedup and routing in the same launches (kv_unique_route_peer); the owners' rows are
+    # padded for the NEXT step under the tail of the current one
+    self.fused_route = os.environ.get("KVHBM_PEER_FUSED_ROUTE", "1") != "0"
+    if self.fused_route:
+      ops.route_fill_peer(G, C, self.seg_ids, self.seg_occ, self.route["counts"])
+      t.cuda.synchronize(self.dev)
+      dist.barrier(group=self.group)
 
   def _barrier(self):
     ops.peer_barrier(self.seg_flags, self.flags, self.bstate, self.rank, self.world,
@@ -334,13 +343,17 @@ class PeerShardedStep(PaddedShardedStep):
     out = self.out if out is None else out
     main = t.cuda.current_stream(self.dev)
     s1, s2 = self.side, self.side2
-    ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
+    if self.fused_route:           # dedup + route = the id exchange, in the same launches
+      ops.unique_route_peer(ids, self.uniq, self.idx, self.cnt, self.num, G, C, self.mode,
+                            self.seg_ids, self.seg_occ, self.route)
+    else:
+      ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
     s2.wait_stream(main)
     with t.cuda.stream(s2):        # sum duplicate gradients locally
       ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
-    # route = the id exchange: ids / counts land in the owners' inboxes
-    ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids, self.seg_occ,
-                       self.route)
+    if not self.fused_route:       # route = the id exchange: ids / counts land in the owners' inboxes
+      ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids,
+                         self.seg_occ, self.route)
     self._barrier()                # A: every peer's ids are in my inbox
     ev_a = t.cuda.Event()
     ev_a.record(main)
@@ -367,6 +380,8 @@ class PeerShardedStep(PaddedShardedStep):
                                                    advance_powers=True)
     with t.cuda.stream(s1):
       s1.wait_event(ev_b)
+      if self.fused_route:         # every owner has read its inbox: pad it for the next step
+        ops.route_fill_peer(G, C, self.seg_ids, self.seg_occ, self.route["counts"])
       ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, out)
     main.wait_stream(s1)
     return out
