@@ -128,3 +128,77 @@ def test_streaming_config_against_oracle():
   var.check_state(rtol=1e-6, atol=1e-7)
   acc.check_state(rtol=1e-6, atol=1e-7)
   kvtest_util.TODAY = TODAY
+
+
+def _export_state(st):
+  k, v, *_rest = ops.kv_variable_export(st.var, first_n=6, enable_cutoff=False, cutoff_value=0.0,
+                                        freq_dtype=torch.int32)
+  ks, vs, *_ = ops.kv_variable_export(st.slot, first_n=6, enable_cutoff=False, cutoff_value=0.0,
+                                      freq_dtype=torch.int32)
+  a = dict(zip(k.cpu().numpy().tolist(), v.cpu().numpy()))
+  b = dict(zip(ks.cpu().numpy().tolist(), vs.cpu().numpy()))
+  return a, b, _rest
+
+
+def test_rotation_graph_equals_step_by_step_and_oracle():
+  """bench.py's pipelined schedule (one graph per rotation, only true dependencies between
+  consecutive steps) leaves the tables as running the steps one after the other does."""
+  keys, D, B, nb = 30000, 64, 4096, bench.N_BATCHES
+  dev = torch.device(DEV)
+  ids_np, grads_np = bench.make_batches(nb, keys, B, D, seed_ids=5, seed_grad=6)
+  states, rows = [], []
+  for mode in ("strict", "rotation"):
+    st = bench.LocalStepper(keys, D, B, dev)
+    st.populate()
+    st.prepare([t(x) for x in ids_np], [t(x) for x in grads_np])   # = one eager pass (16 steps)
+    assert st.rotation is not None
+    if mode == "strict":
+      for i in range(2 * nb + 3):
+        st.step(i)
+    else:
+      st.run_steps(2 * nb + 3)                                      # 2 rotations + 3 single steps
+    torch.cuda.synchronize()
+    states.append(_export_state(st))
+    rows.append([b["rows"].cpu().numpy().copy() for b in st.bufs])
+    hp = st.hp.cpu().numpy().copy()
+    ops.destroy_kv_variable_op_v2(st.var)
+    ops.destroy_kv_variable_op_v2(st.slot)
+  (va, sa, _), (vb, sb, _) = states
+  assert va.keys() == vb.keys() and sa.keys() == sb.keys()
+  # not bit for bit: the gradient sums add rows with float atomics, whose order varies from
+  # launch to launch; a missing dependency would show up at the size of an update (1e-2)
+  ks = sorted(va)
+  np.testing.assert_allclose(np.stack([va[k] for k in ks]), np.stack([vb[k] for k in ks]),
+                             rtol=2e-5, atol=1e-6)
+  np.testing.assert_allclose(np.stack([sa[k] for k in ks]), np.stack([sb[k] for k in ks]),
+                             rtol=2e-5, atol=1e-6)
+  for ra, rb in zip(*rows):
+    np.testing.assert_allclose(ra, rb, rtol=2e-5, atol=1e-6)
+  # and both equal the oracle run over the same 3 * nb + 3 steps (1e-6, DESIGN.md §3)
+  var = ob.OracleTable(D, 0, seed=1)
+  var.set_init_table(bench.init_table(D))
+  slot = ob.OracleTable(3 * D, 0, seed=1)
+  slot.set_init_table(np.zeros((bench.INIT_ROWS, 3 * D), np.float32))
+  allk = np.arange(keys, dtype=np.int64)
+  var.gather_or_insert(allk, today=TODAY)
+  slot.gather_or_insert(allk, today=TODAY)
+  h = bench.HP
+  b1p, b2p = np.float32(h["beta1"]), np.float32(h["beta2"])
+  last_rows = None
+  for i in range(3 * nb + 3):
+    ids, grad = ids_np[i % nb], grads_np[i % nb]
+    last_rows = var.gather_or_insert(ids, today=TODAY)
+    u, idx = ob.unique(ids)
+    ob.apply_group_adam_v4(var, slot, u, ob.segment_sum(grad, idx, u.size), h["lr"], float(b1p),
+                           float(b2p), h["beta1"], h["beta2"], h["epsilon"], h["l1"], h["l2"],
+                           h["l21"], today=TODAY)
+    b1p, b2p = b1p * np.float32(h["beta1"]), b2p * np.float32(h["beta2"])
+  assert hp[1] == b1p and hp[2] == b2p
+  ref = var.export(first_n=6, enable_cutoff=False, cutoff_value=0.0, freq_u32=True)
+  ref_rows = dict(zip(ref["keys"].tolist(), ref["values"]))
+  assert ref_rows.keys() == vb.keys()
+  got = np.stack([vb[k] for k in sorted(vb)])
+  want = np.stack([ref_rows[k] for k in sorted(vb)])
+  np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-6)
+  np.testing.assert_allclose(rows[1][(3 * nb + 2) % nb], last_rows.reshape(B, D), rtol=2e-5,
+                             atol=1e-6)

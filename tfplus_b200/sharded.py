@@ -319,8 +319,6 @@ class PeerShardedStep(PaddedShardedStep):
     self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
     self.side2 = t.cuda.Stream(device=self.dev)
-    if os.environ.get("KVHBM_PEER_PRIO", "0") == "1":   # owner dedup is the critical branch
-      self.side = t.cuda.Stream(device=self.dev, priority=-1)
     self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
     # dedup and routing in the same launches (kv_unique_route_peer); the owners' rows are
     # padded for the NEXT step under the tail of the current one
