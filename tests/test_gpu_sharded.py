@@ -269,13 +269,16 @@ def test_peer_variants_equal_the_local_ones_on_one_gpu():
     ops.peer_barrier(_segments(flags, 1), flags, state, 3, 2)
 
 
+NSTEPS = 4
+
+
 def _padded_worker(rank, world, port, q, use_graph, exchange="nccl"):
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
   torch.cuda.set_device(rank)
   dev = torch.device("cuda", rank)
   dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
   from tfplus_b200.sharded import PaddedShardedStep, PeerShardedStep
-  Step = PeerShardedStep if exchange == "peer" else PaddedShardedStep
+  Step = PeerShardedStep if exchange.startswith("peer") else PaddedShardedStep
   ops.set_today(TODAY)
   var = ops.kv_variable(value_shape=[D], enter_threshold=0, device=dev, seed=5, capacity_hint=4096)
   slot = ops.kv_variable(value_shape=[3 * D], device=dev, seed=5, capacity_hint=4096)
@@ -284,35 +287,56 @@ def _padded_worker(rank, world, port, q, use_graph, exchange="nccl"):
   hp = torch.tensor([0.05, 0.9, 0.999, 0.9, 0.999, 1e-8, 1e-5, 1e-5, 1e-5], device=dev)
   betas = torch.tensor([0.9, 0.999], device=dev)
   step = Step(var, slot, D, 400, world, rank, dev, hp, betas, cap=256)
-  data = [batches(world, s) for s in range(3)]
+  data = [batches(world, s) for s in range(NSTEPS)]
   ids = [torch.from_numpy(d[0][rank]).to(dev) for d in data]
   grads = [torch.from_numpy(d[1][rank]).to(dev) for d in data]
-  looked = []
-  if use_graph:
+  looked = {}
+  if exchange == "peer_rotation":
+    # the pipelined schedule: steps issued together, only true dependencies between them
+    first = 0
+    if use_graph:
+      for s in (0, 1):                    # strict steps first: the two schedules must mix
+        looked[s] = step.run(ids[s], grads[s]).cpu().numpy().copy()
+      first = 2
+      torch.cuda.synchronize()
+      side = torch.cuda.Stream(device=dev)
+      side.wait_stream(torch.cuda.current_stream(dev))
+      with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+          step.run_rotation(ids[first:], grads[first:])
+      torch.cuda.current_stream(dev).wait_stream(side)
+      g.replay()
+      torch.cuda.synchronize()
+      del g
+    else:
+      step.run_rotation(ids, grads)
+    looked[NSTEPS - 1] = step.out.cpu().numpy().copy()
+  elif use_graph:
     step.run(ids[0], grads[0])            # eager warm-up = step 0
-    looked.append(step.out.cpu().numpy().copy())
+    looked[0] = step.out.cpu().numpy().copy()
     torch.cuda.synchronize()
     graphs = []
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-      for s in (1, 2):
+      for s in range(1, NSTEPS):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
           step.run(ids[s], grads[s])
         graphs.append(g)
     torch.cuda.current_stream(dev).wait_stream(side)
-    for g in graphs:
+    for s, g in enumerate(graphs, 1):
       g.replay()
       torch.cuda.synchronize()
-      looked.append(step.out.cpu().numpy().copy())
+      looked[s] = step.out.cpu().numpy().copy()
     del graphs, g          # captured NCCL work must be gone before the process group is torn down
     torch.cuda.synchronize()
   else:
-    for s in range(3):
-      looked.append(step.run(ids[s], grads[s]).cpu().numpy().copy())
+    for s in range(NSTEPS):
+      looked[s] = step.run(ids[s], grads[s]).cpu().numpy().copy()
   assert not step.overflowed()
-  if exchange == "peer":
+  if exchange.startswith("peer"):
     assert step.barrier_timeouts() == 0
   k, v, _, _, fk, fv = ops.kv_variable_export(var, first_n=6, enable_cutoff=True,
                                               cutoff_value=1e-20, freq_dtype=torch.int32)
@@ -323,7 +347,7 @@ def _padded_worker(rank, world, port, q, use_graph, exchange="nccl"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "peer_rotation"])
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_padded_sharded_step_equals_one_table(use_graph, exchange):
   world = 2
@@ -342,14 +366,15 @@ def test_padded_sharded_step_equals_one_table(use_graph, exchange):
   slot = ob.OracleTable(3 * D, 0, seed=5)
   slot.set_init_table(np.zeros((16, 3 * D), np.float32))
   b1p, b2p = np.float32(0.9), np.float32(0.999)
-  for step in range(3):
+  for step in range(NSTEPS):
     ids_all, grads_all = batches(world, step)
     ids, grad = np.concatenate(ids_all), np.concatenate(grads_all)
     rows = var.gather_or_insert(ids, today=TODAY)
     off = 0
     for r in range(world):
       n = ids_all[r].size
-      np.testing.assert_allclose(results[r][1][step], rows[off:off + n], rtol=1e-6, atol=1e-7)
+      if step in results[r][1]:
+        np.testing.assert_allclose(results[r][1][step], rows[off:off + n], rtol=1e-6, atol=1e-7)
       off += n
     u, idx = ob.unique(ids)
     ob.apply_group_adam_v4(var, slot, u, ob.segment_sum(grad, idx, u.size), 0.05, float(b1p),

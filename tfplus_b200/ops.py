@@ -713,10 +713,10 @@ def route_ids_peer(ids, occ, num_shards, capacity, mode, num_ids, seg_ids, seg_o
 
 
 def unique_route_peer(ids, uniq, idx, counts, num, num_shards, capacity, mode, seg_ids, seg_occ,
-                      out):
+                      out, ws=None):
   """kv_unique_route_peer: unique_into + route_ids_peer in the same launches;
   out = dict(perm, counts (per shard, zeroed by route_fill_peer), overflow)."""
-  ws = Workspace.get(ids.device)
+  ws = ws or Workspace.get(ids.device)
   with torch.cuda.device(ids.device):
     check(_lib.load().kv_unique_route_peer(ws.ptr, ids.data_ptr(), ids.numel(), uniq.data_ptr(),
                                            idx.data_ptr(), _ptr(counts), num.data_ptr(),
@@ -760,9 +760,10 @@ def peer_barrier(peer_flags, my_flags, state, rank, world, timeout_ms=2000):
                                       _stream(my_flags.device)))
 
 
-def unique_into(ids, uniq, idx, counts, num):
-  """kv_unique into caller-owned buffers (graph-capturable: nothing is allocated or read back)."""
-  ws = Workspace.get(ids.device)
+def unique_into(ids, uniq, idx, counts, num, ws=None):
+  """kv_unique into caller-owned buffers (graph-capturable: nothing is allocated or read back).
+  Calls that may run concurrently on one device need a Workspace each (`ws`)."""
+  ws = ws or Workspace.get(ids.device)
   with torch.cuda.device(ids.device):
     check(_lib.load().kv_unique(ws.ptr, ids.data_ptr(), ids.numel(), uniq.data_ptr(),
                                 idx.data_ptr(), _ptr(counts), num.data_ptr(),

@@ -280,53 +280,71 @@ class PeerMemory:
 class PeerShardedStep(PaddedShardedStep):
   """PaddedShardedStep without NCCL in the data path: every exchange is the stores of the
   kernel that produces the data, written straight into the destination GPU's buffer over
-  NVLink (kv_route_ids_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the only
+  NVLink (kv_unique_route_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the only
   cross-GPU synchronisation is two kv_peer_barrier kernels per step:
 
-    unique -> route ==ids==> | barrier A | owner lookup ==rows==>      | barrier B | expand rows
-           -> local grad sums            | grad sums    ==grads==>     |           | owner sum, apply
-                                         | owner-side dedup            |
+    unique+route ==ids==> | barrier A | owner lookup ==rows==>      | barrier B | expand rows
+           -> local grad sums         | grad sums    ==grads==>     |           | owner sum, apply
+                                      | owner-side dedup            |
 
   (ids and gradients are both inputs of the step, as in the single-GPU step, so the gradient
   exchange shares barrier B with the rows.)  Buffer reuse across steps needs no extra barrier:
-  a rank stores into a peer's inbox only after barrier B of the step before, which the peer
-  reaches after its last read of the inbox; into a peer's row / gradient buffers only after
-  barrier A, which the peer reaches after the previous step's expand / owner sum."""
+  a rank stores into a peer's inbox only after barrier B of an earlier step, which the peer
+  reaches after its last read of that inbox; into a peer's row / gradient buffers only after
+  barrier A, which the peer reaches after the previous step's expand / owner sum.
+
+  `run` is one step, strictly after the previous one.  `run_rotation` issues a list of steps
+  with only their true dependencies (the requester-side dedup, routing and gradient sum of
+  step t+1 run under the owner phase of step t): two inboxes and two sets of requester-side
+  buffers alternate, everything else is ordered by the barriers."""
 
   def __init__(self, *a, **kw):
     super().__init__(*a, **kw)
     t = torch
-    G, C, D, r = self.world, self.cap, self.dim, self.rank
+    B, G, C, D, r = self.batch, self.world, self.cap, self.dim, self.rank
     al = lambda x: (x + 255) // 256 * 256
     o_flags = 0
-    o_ids = al(4 * G)
-    o_occ = o_ids + al(G * C * 8)
-    o_rows = o_occ + al(G * C * 4)
+    o_ids = [al(4 * G), 0]
+    o_ids[1] = o_ids[0] + al(G * C * 8)
+    o_occ = [o_ids[1] + al(G * C * 8), 0]
+    o_occ[1] = o_occ[0] + al(G * C * 4)
+    o_rows = o_occ[1] + al(G * C * 4)
     o_grads = o_rows + al(G * C * D * 4)
     total = o_grads + al(G * C * D * 4)
     self.peer = PeerMemory(total, self.dev, self.group)
     pm = self.peer
     self.flags = pm.local(o_flags, (G,), t.int32)
-    self.ids_in = pm.local(o_ids, (G * C,), t.int64)
-    self.occ_in = pm.local(o_occ, (G * C,), t.int32)
+    self.ids_in = [pm.local(o, (G * C,), t.int64) for o in o_ids]     # two inboxes
+    self.occ_in = [pm.local(o, (G * C,), t.int32) for o in o_occ]
     self.rows_in = pm.local(o_rows, (G * C, D), t.float32)
     self.grads_in = pm.local(o_grads, (G * C, D), t.float32)
     self.seg_flags = pm.table(o_flags)
-    self.seg_ids = pm.table(o_ids + r * C * 8)
-    self.seg_occ = pm.table(o_occ + r * C * 4)
+    self.seg_ids = [pm.table(o + r * C * 8) for o in o_ids]
+    self.seg_occ = [pm.table(o + r * C * 4) for o in o_occ]
     self.seg_rows = pm.table(o_rows + r * C * D * 4)
     self.seg_grads = pm.table(o_grads + r * C * D * 4)
     self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
     self.side2 = t.cuda.Stream(device=self.dev)
+    self.side3 = t.cuda.Stream(device=self.dev)
     self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
-    # dedup and routing in the same launches (kv_unique_route_peer); the owners' rows are
-    # padded for the NEXT step under the tail of the current one
+    # requester-side buffers, two sets (set 0 = the ones `run` uses)
+    i64 = dict(dtype=t.int64, device=self.dev)
+    i32 = dict(dtype=t.int32, device=self.dev)
+    self.sets = [dict(uniq=self.uniq, idx=self.idx, cnt=self.cnt, num=self.num, gsum=self.gsum,
+                      route=self.route),
+                 dict(uniq=t.empty(B, **i64), idx=t.empty(B, **i32), cnt=t.empty(B, **i32),
+                      num=t.zeros(1, **i32), gsum=t.empty(B, D, dtype=t.float32, device=self.dev),
+                      route={"perm": t.empty(B, **i32), "counts": t.empty(G, **i32),
+                             "overflow": self.route["overflow"]})]
+    self.ws_owner = ops.Workspace(self.dev)     # owner-side dedup runs beside the requester's
+    # dedup and routing share their launches (kv_unique_route_peer); the owners' inboxes are
+    # padded ahead of time, under the tail of an earlier step
     self.fused_route = os.environ.get("KVHBM_PEER_FUSED_ROUTE", "1") != "0"
-    if self.fused_route:
-      ops.route_fill_peer(G, C, self.seg_ids, self.seg_occ, self.route["counts"])
-      t.cuda.synchronize(self.dev)
-      dist.barrier(group=self.group)
+    for p in range(2):
+      ops.route_fill_peer(G, C, self.seg_ids[p], self.seg_occ[p], self.sets[p]["route"]["counts"])
+    t.cuda.synchronize(self.dev)
+    dist.barrier(group=self.group)
 
   def _barrier(self):
     ops.peer_barrier(self.seg_flags, self.flags, self.bstate, self.rank, self.world,
@@ -334,6 +352,13 @@ class PeerShardedStep(PaddedShardedStep):
 
   def barrier_timeouts(self):
     return int(self.bstate[1].item())
+
+  def _owner_update(self):
+    ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
+                             accumulate=True)
+    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
+                                                   self.hpt, num_indices=self.o_num,
+                                                   advance_powers=True)
 
   def run(self, ids, grad, out=None):
     B, G, C, D = self.batch, self.world, self.cap, self.dim
@@ -343,27 +368,30 @@ class PeerShardedStep(PaddedShardedStep):
     s1, s2 = self.side, self.side2
     if self.fused_route:           # dedup + route = the id exchange, in the same launches
       ops.unique_route_peer(ids, self.uniq, self.idx, self.cnt, self.num, G, C, self.mode,
-                            self.seg_ids, self.seg_occ, self.route)
+                            self.seg_ids[0], self.seg_occ[0], self.route)
     else:
       ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
     s2.wait_stream(main)
     with t.cuda.stream(s2):        # sum duplicate gradients locally
       ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
     if not self.fused_route:       # route = the id exchange: ids / counts land in the owners' inboxes
-      ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids,
-                         self.seg_occ, self.route)
+      ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
+      ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids[0],
+                         self.seg_occ[0], self.route)
     self._barrier()                # A: every peer's ids are in my inbox
     ev_a = t.cuda.Event()
     ev_a.record(main)
     with t.cuda.stream(s1):        # owner-side dedup of what the peers sent
       s1.wait_event(ev_a)
-      ops.unique_into(self.ids_in, self.o_uniq, self.o_idx, None, self.o_num)
+      ops.unique_into(self.ids_in[0], self.o_uniq, self.o_idx, None, self.o_num,
+                      ws=self.ws_owner)
     with t.cuda.stream(s2):        # gradient exchange: sums go to the owners' buffers
       s2.wait_event(ev_a)
       ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads, C)
       ops.zero_rows(self.o_gsum)
     # owner lookup = the row exchange: rows land in the requesters' buffers
-    ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in, self.occ_in, self.seg_rows, C)
+    ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[0], self.occ_in[0],
+                                          self.seg_rows, C)
     main.wait_stream(s1)
     main.wait_stream(s2)
     self._barrier()                # B: my rows and every peer's gradient sums have arrived
@@ -371,17 +399,77 @@ class PeerShardedStep(PaddedShardedStep):
     ev_b.record(main)
     # the longer branch is issued first: a captured graph keeps the first dependent of a node
     # on the node's own stream and pays ~5 us of cross-stream latency for the others
-    ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
-                             accumulate=True)
-    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
-                                                   self.hpt, num_indices=self.o_num,
-                                                   advance_powers=True)
+    self._owner_update()
     with t.cuda.stream(s1):
       s1.wait_event(ev_b)
       if self.fused_route:         # every owner has read its inbox: pad it for the next step
-        ops.route_fill_peer(G, C, self.seg_ids, self.seg_occ, self.route["counts"])
+        ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
       ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, out)
     main.wait_stream(s1)
+    return out
+
+  def run_rotation(self, ids_list, grad_list, out=None):
+    """len(ids_list) (even) consecutive steps with only their true dependencies.  Streams:
+    main = barrier A, owner dedup, barrier B, owner sum, apply (the critical chain, step after
+    step); s_r = requester chain (dedup+route and local gradient sum of step t, then, once
+    barrier A(t) has passed, the gradient exchange of step t, then step t+1's dedup ...);
+    s_g = owner lookup; s_e = inbox padding and row expansion."""
+    assert len(ids_list) % 2 == 0 and self.fused_route
+    B, G, C, D = self.batch, self.world, self.cap, self.dim
+    t = torch
+    out = self.out if out is None else out
+    main = t.cuda.current_stream(self.dev)
+    s_r, s_g, s_e = self.side, self.side2, self.side3
+    for s in (s_r, s_g, s_e):
+      s.wait_stream(main)
+    ev_e = [None, None]            # expand of the last step that used requester set p
+    ev_e_prev = None               # expand of the previous step (rows_in is single)
+    for step, (ids, grad) in enumerate(zip(ids_list, grad_list)):
+      p = step & 1
+      S = self.sets[p]
+      with t.cuda.stream(s_r):     # requester: nothing here depends on the table
+        if ev_e[p] is not None:
+          s_r.wait_event(ev_e[p])  # set p's perm / idx were still being read by that expand
+        ops.unique_route_peer(ids, S["uniq"], S["idx"], S["cnt"], S["num"], G, C, self.mode,
+                              self.seg_ids[p], self.seg_occ[p], S["route"])
+        ev_r1 = t.cuda.Event()
+        ev_r1.record(s_r)
+        ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"])
+      main.wait_event(ev_r1)       # my ids are stored before I say so
+      if ev_e_prev is not None:
+        main.wait_event(ev_e_prev) # the owners may overwrite rows_in after this barrier
+      self._barrier()              # A
+      ev_a = t.cuda.Event()
+      ev_a.record(main)
+      ops.unique_into(self.ids_in[p], self.o_uniq, self.o_idx, None, self.o_num,
+                      ws=self.ws_owner)
+      with t.cuda.stream(s_g):
+        s_g.wait_event(ev_a)
+        ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[p], self.occ_in[p],
+                                              self.seg_rows, C)
+        ops.zero_rows(self.o_gsum)
+        ev_g = t.cuda.Event()
+        ev_g.record(s_g)
+      with t.cuda.stream(s_r):
+        s_r.wait_event(ev_a)       # the owners are done with the previous step's sums
+        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads, C)
+        ev_r3 = t.cuda.Event()
+        ev_r3.record(s_r)
+      main.wait_event(ev_g)
+      main.wait_event(ev_r3)
+      self._barrier()              # B
+      ev_b = t.cuda.Event()
+      ev_b.record(main)
+      self._owner_update()
+      with t.cuda.stream(s_e):
+        s_e.wait_event(ev_b)
+        ops.route_fill_peer(G, C, self.seg_ids[p], self.seg_occ[p], S["route"]["counts"])
+        ops.expand_rows(self.rows_in, S["route"]["perm"], S["idx"], B, out)
+        ev_e[p] = t.cuda.Event()
+        ev_e[p].record(s_e)
+        ev_e_prev = ev_e[p]
+    for s in (s_r, s_g, s_e):
+      main.wait_stream(s)
     return out
 
 
@@ -473,18 +561,30 @@ class ShardedStepper:
       raise RuntimeError("padded shard exchange overflowed: raise cap")
     ops.kv_variable_reserve(self.tbl.var, 2 * self.padded.cap * self.world)
     ops.kv_variable_reserve(self.tbl.slots[0], 2 * self.padded.cap * self.world)
-    self.graphs = []
-    if os.environ.get("KVHBM_SHARDED_GRAPH", "1") != "0":
-      side = t.cuda.Stream(device=self.dev)
-      side.wait_stream(t.cuda.current_stream(self.dev))
-      with t.cuda.stream(side):
-        for i in range(len(ids_d)):
-          g = t.cuda.CUDAGraph()
-          with t.cuda.graph(g, stream=side):
-            self.padded.run(ids_d[i], grads_d[i])
-          self.graphs.append(g)
-      t.cuda.current_stream(self.dev).wait_stream(side)
+    self.graphs = [self._capture(lambda i=i: self.padded.run(ids_d[i], grads_d[i]))
+                   for i in range(len(ids_d))]
+    if self.graphs and self.graphs[0] is None:
+      self.graphs = []
+    # the pipelined schedule: one graph per rotation of the batches (PeerShardedStep only)
+    self.rotation = None
+    if (self.graphs and hasattr(self.padded, "run_rotation") and self.padded.fused_route
+        and len(ids_d) % 2 == 0 and os.environ.get("KVHBM_BENCH_PIPELINE", "1") != "0"):
+      self.padded.run_rotation(ids_d, grads_d)        # once eagerly: errors surface here
       t.cuda.synchronize()
+      self.rotation = self._capture(lambda: self.padded.run_rotation(ids_d, grads_d))
+    t.cuda.synchronize()
+
+  def run_steps(self, K):
+    """K consecutive steps: whole rotations as one graph each, the rest step by step."""
+    n, i = len(self.ids_d), 0
+    if self.rotation is not None:
+      while K - i >= n:
+        self.rotation.replay()
+        i += n
+      self.steps_done += i
+    while i < K:
+      self.step(i)
+      i += 1
 
   def step(self, i):
     k = i % len(self.ids_d)
@@ -497,6 +597,7 @@ class ShardedStepper:
   def release(self):
     self.graphs = []
     self.e2e = []
+    self.rotation = None
 
   def stage_times(self, steps):
     t = self.torch
