@@ -22,8 +22,15 @@ st.prepare(ids, gr)
 for i in range(5): st.step(i)
 torch.cuda.synchronize(); dist.barrier()
 from torch.profiler import profile, ProfilerActivity
+PIPE = os.environ.get("PIPE", "0") == "1" and getattr(st, "rotation", None) is not None
+if PIPE:
+  st.run_steps(8)
+  torch.cuda.synchronize(); dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-  for i in range(10): st.step(i)
+  if PIPE:
+    st.run_steps(12)          # 3 rotations of the 4 batches; table below is per 10 -> scale by eye
+  else:
+    for i in range(10): st.step(i)
   torch.cuda.synchronize()
 if rank == 0:
   rows = []
@@ -41,8 +48,8 @@ if rank == 0:
   prof.export_chrome_trace(path)
   ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
   ev.sort(key=lambda e: e["ts"])
-  per_step = max(1, len(ev) // 10)
-  tail = ev[-2 * per_step:]
+  per_step = max(1, len(ev) // (12 if PIPE else 10))
+  tail = ev[-(4 if PIPE else 2) * per_step:]
   t0 = tail[0]["ts"]
   print("timeline (last 2 steps, %d kernels per step):" % per_step)
   for e in tail:

@@ -303,32 +303,35 @@ class PeerShardedStep(PaddedShardedStep):
     t = torch
     B, G, C, D, r = self.batch, self.world, self.cap, self.dim, self.rank
     al = lambda x: (x + 255) // 256 * 256
-    o_flags = 0
-    o_ids = [al(4 * G), 0]
-    o_ids[1] = o_ids[0] + al(G * C * 8)
-    o_occ = [o_ids[1] + al(G * C * 8), 0]
-    o_occ[1] = o_occ[0] + al(G * C * 4)
-    o_rows = o_occ[1] + al(G * C * 4)
-    o_grads = o_rows + al(G * C * D * 4)
-    total = o_grads + al(G * C * D * 4)
-    self.peer = PeerMemory(total, self.dev, self.group)
+    # one symmetric allocation: 2 barrier channels, and two of every exchange buffer (the
+    # pipelined schedule alternates them; `run` uses the first of each)
+    off, cur = {}, 0
+    for name, nbytes in (("flags", 4 * G), ("ids", G * C * 8), ("occ", G * C * 4),
+                         ("rows", G * C * D * 4), ("grads", G * C * D * 4)):
+      off[name] = []
+      for _ in range(2):
+        off[name].append(cur)
+        cur += al(nbytes)
+    self.peer = PeerMemory(cur, self.dev, self.group)
     pm = self.peer
-    self.flags = pm.local(o_flags, (G,), t.int32)
-    self.ids_in = [pm.local(o, (G * C,), t.int64) for o in o_ids]     # two inboxes
-    self.occ_in = [pm.local(o, (G * C,), t.int32) for o in o_occ]
-    self.rows_in = pm.local(o_rows, (G * C, D), t.float32)
-    self.grads_in = pm.local(o_grads, (G * C, D), t.float32)
-    self.seg_flags = pm.table(o_flags)
-    self.seg_ids = [pm.table(o + r * C * 8) for o in o_ids]
-    self.seg_occ = [pm.table(o + r * C * 4) for o in o_occ]
-    self.seg_rows = pm.table(o_rows + r * C * D * 4)
-    self.seg_grads = pm.table(o_grads + r * C * D * 4)
-    self.bstate = t.zeros(2, dtype=t.int32, device=self.dev)
+    self.flags = [pm.local(o, (G,), t.int32) for o in off["flags"]]
+    self.ids_in = [pm.local(o, (G * C,), t.int64) for o in off["ids"]]
+    self.occ_in = [pm.local(o, (G * C,), t.int32) for o in off["occ"]]
+    self.rows_in = [pm.local(o, (G * C, D), t.float32) for o in off["rows"]]
+    self.grads_in = [pm.local(o, (G * C, D), t.float32) for o in off["grads"]]
+    self.seg_flags = [pm.table(o) for o in off["flags"]]
+    self.seg_ids = [pm.table(o + r * C * 8) for o in off["ids"]]
+    self.seg_occ = [pm.table(o + r * C * 4) for o in off["occ"]]
+    self.seg_rows = [pm.table(o + r * C * D * 4) for o in off["rows"]]
+    self.seg_grads = [pm.table(o + r * C * D * 4) for o in off["grads"]]
+    self.bstate = [t.zeros(2, dtype=t.int32, device=self.dev) for _ in range(2)]
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
     self.side2 = t.cuda.Stream(device=self.dev)
     self.side3 = t.cuda.Stream(device=self.dev)
+    self.side4 = t.cuda.Stream(device=self.dev)
+    self.side5 = t.cuda.Stream(device=self.dev)
     self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
-    # requester-side buffers, two sets (set 0 = the ones `run` uses)
+    # requester-side and owner-side dedup buffers, two sets (set 0 = the ones `run` uses)
     i64 = dict(dtype=t.int64, device=self.dev)
     i32 = dict(dtype=t.int32, device=self.dev)
     self.sets = [dict(uniq=self.uniq, idx=self.idx, cnt=self.cnt, num=self.num, gsum=self.gsum,
@@ -337,6 +340,9 @@ class PeerShardedStep(PaddedShardedStep):
                       num=t.zeros(1, **i32), gsum=t.empty(B, D, dtype=t.float32, device=self.dev),
                       route={"perm": t.empty(B, **i32), "counts": t.empty(G, **i32),
                              "overflow": self.route["overflow"]})]
+    self.osets = [dict(uniq=self.o_uniq, idx=self.o_idx, num=self.o_num),
+                  dict(uniq=t.empty(G * C, **i64), idx=t.empty(G * C, **i32),
+                       num=t.zeros(1, **i32))]
     self.ws_owner = ops.Workspace(self.dev)     # owner-side dedup runs beside the requester's
     # dedup and routing share their launches (kv_unique_route_peer); the owners' inboxes are
     # padded ahead of time, under the tail of an earlier step
@@ -346,18 +352,21 @@ class PeerShardedStep(PaddedShardedStep):
     t.cuda.synchronize(self.dev)
     dist.barrier(group=self.group)
 
-  def _barrier(self):
-    ops.peer_barrier(self.seg_flags, self.flags, self.bstate, self.rank, self.world,
-                     self.barrier_ms)
+  def _barrier(self, channel=1):
+    """Barriers of one channel must be issued in the same order on every rank; the pipelined
+    schedule runs its A barriers (channel 0) on another stream than its B barriers (1)."""
+    ops.peer_barrier(self.seg_flags[channel], self.flags[channel], self.bstate[channel],
+                     self.rank, self.world, self.barrier_ms)
 
   def barrier_timeouts(self):
-    return int(self.bstate[1].item())
+    return int(self.bstate[0][1].item()) + int(self.bstate[1][1].item())
 
-  def _owner_update(self):
-    ops.unsorted_segment_sum(self.grads_in, self.o_idx, self.o_num, out=self.o_gsum,
+  def _owner_update(self, p=0):
+    O = self.osets[p]
+    ops.unsorted_segment_sum(self.grads_in[p], O["idx"], O["num"], out=self.o_gsum,
                              accumulate=True)
-    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
-                                                   self.hpt, num_indices=self.o_num,
+    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, O["uniq"],
+                                                   self.hpt, num_indices=O["num"],
                                                    advance_powers=True)
 
   def run(self, ids, grad, out=None):
@@ -387,11 +396,11 @@ class PeerShardedStep(PaddedShardedStep):
                       ws=self.ws_owner)
     with t.cuda.stream(s2):        # gradient exchange: sums go to the owners' buffers
       s2.wait_event(ev_a)
-      ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads, C)
+      ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads[0], C)
       ops.zero_rows(self.o_gsum)
     # owner lookup = the row exchange: rows land in the requesters' buffers
     ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[0], self.occ_in[0],
-                                          self.seg_rows, C)
+                                          self.seg_rows[0], C)
     main.wait_stream(s1)
     main.wait_stream(s2)
     self._barrier()                # B: my rows and every peer's gradient sums have arrived
@@ -404,71 +413,93 @@ class PeerShardedStep(PaddedShardedStep):
       s1.wait_event(ev_b)
       if self.fused_route:         # every owner has read its inbox: pad it for the next step
         ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
-      ops.expand_rows(self.rows_in, self.route["perm"], self.idx, B, out)
+      ops.expand_rows(self.rows_in[0], self.route["perm"], self.idx, B, out)
     main.wait_stream(s1)
     return out
 
   def run_rotation(self, ids_list, grad_list, out=None):
-    """len(ids_list) (even) consecutive steps with only their true dependencies.  Streams:
-    main = barrier A, owner dedup, barrier B, owner sum, apply (the critical chain, step after
-    step); s_r = requester chain (dedup+route and local gradient sum of step t, then, once
-    barrier A(t) has passed, the gradient exchange of step t, then step t+1's dedup ...);
-    s_g = owner lookup; s_e = inbox padding and row expansion."""
+    """len(ids_list) (even) consecutive steps with only their true dependencies.
+
+    The one chain that must run step after step is  lookup(t) -> barrier B(t) -> owner sum(t)
+    -> apply(t) -> lookup(t+1)  (a lookup reads what the previous apply wrote); it is issued on
+    the calling stream.  Everything else is fed to it from the side:
+      s_r  requester: dedup+route(t) [= id exchange], step after step;
+      s_g  local gradient sum(t) and - once barrier B(t-1) has passed - the gradient exchange(t);
+      s_o  barrier A(t) (channel 0: every peer's ids(t) are in my inbox) and the owner-side
+           dedup(t), which therefore runs under the owner phase of step t-1;
+      s_e  after barrier B(t): pad the inbox for step t+2, expand the rows of step t.
+    Step t uses buffer set t % 2 of everything exchanged.  Who may overwrite what, and why it
+    is safe, is argued hazard by hazard in DESIGN.md (section 6)."""
     assert len(ids_list) % 2 == 0 and self.fused_route
     B, G, C, D = self.batch, self.world, self.cap, self.dim
     t = torch
     out = self.out if out is None else out
     main = t.cuda.current_stream(self.dev)
-    s_r, s_g, s_e = self.side, self.side2, self.side3
-    for s in (s_r, s_g, s_e):
+    s_r, s_o, s_e, s_z, s_g = self.side, self.side2, self.side3, self.side4, self.side5
+    for s in (s_r, s_o, s_e, s_z, s_g):
       s.wait_stream(main)
-    ev_e = [None, None]            # expand of the last step that used requester set p
-    ev_e_prev = None               # expand of the previous step (rows_in is single)
+    ev_e = [None, None]       # expand (+ inbox padding) of the last step on buffer set p
+    ev_r3 = [None, None]      # gradient exchange of the last step on buffer set p
+    ev_apply = [None, None]   # apply of the last step on buffer set p
+    ev_b_prev = None          # barrier B of the previous step
     for step, (ids, grad) in enumerate(zip(ids_list, grad_list)):
       p = step & 1
-      S = self.sets[p]
+      S, O = self.sets[p], self.osets[p]
       with t.cuda.stream(s_r):     # requester: nothing here depends on the table
         if ev_e[p] is not None:
-          s_r.wait_event(ev_e[p])  # set p's perm / idx were still being read by that expand
+          s_r.wait_event(ev_e[p])  # set p's perm / idx were read, and inbox p padded, by then
+          s_r.wait_event(ev_r3[p])
         ops.unique_route_peer(ids, S["uniq"], S["idx"], S["cnt"], S["num"], G, C, self.mode,
                               self.seg_ids[p], self.seg_occ[p], S["route"])
         ev_r1 = t.cuda.Event()
         ev_r1.record(s_r)
+      with t.cuda.stream(s_g):     # gradients: local sums, then the exchange (own chain, so the
+        s_g.wait_event(ev_r1)      # next step's dedup does not queue behind barrier B(t-1))
         ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"])
-      main.wait_event(ev_r1)       # my ids are stored before I say so
-      if ev_e_prev is not None:
-        main.wait_event(ev_e_prev) # the owners may overwrite rows_in after this barrier
-      self._barrier()              # A
-      ev_a = t.cuda.Event()
-      ev_a.record(main)
-      ops.unique_into(self.ids_in[p], self.o_uniq, self.o_idx, None, self.o_num,
-                      ws=self.ws_owner)
-      with t.cuda.stream(s_g):
-        s_g.wait_event(ev_a)
-        ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[p], self.occ_in[p],
-                                              self.seg_rows, C)
+        if ev_b_prev is not None:
+          s_g.wait_event(ev_b_prev)  # the owners have passed B(t-1): done with grads_in[p] of t-2
+        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads[p], C)
+        ev_r3[p] = t.cuda.Event()
+        ev_r3[p].record(s_g)
+      with t.cuda.stream(s_o):
+        s_o.wait_event(ev_r1)      # my ids are stored before I say so
+        self._barrier(0)           # A(t)
+        ev_a = t.cuda.Event()
+        ev_a.record(s_o)
+        if ev_apply[p] is not None:
+          s_o.wait_event(ev_apply[p])   # owner set p was read by that apply
+        ops.unique_into(self.ids_in[p], O["uniq"], O["idx"], None, O["num"], ws=self.ws_owner)
+        ev_ub = t.cuda.Event()
+        ev_ub.record(s_o)
+      with t.cuda.stream(s_z):     # the sums' destination: free once the previous apply is done
+        if ev_apply[1 - p] is not None:
+          s_z.wait_event(ev_apply[1 - p])
         ops.zero_rows(self.o_gsum)
-        ev_g = t.cuda.Event()
-        ev_g.record(s_g)
-      with t.cuda.stream(s_r):
-        s_r.wait_event(ev_a)       # the owners are done with the previous step's sums
-        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads, C)
-        ev_r3 = t.cuda.Event()
-        ev_r3.record(s_r)
-      main.wait_event(ev_g)
-      main.wait_event(ev_r3)
-      self._barrier()              # B
+        ev_z = t.cuda.Event()
+        ev_z.record(s_z)
+      # ---- the serial chain ----
+      main.wait_event(ev_a)
+      ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[p], self.occ_in[p],
+                                            self.seg_rows[p], C)
+      main.wait_event(ev_ub)       # arriving at B also says: I am done reading inbox p
+      main.wait_event(ev_r3[p])    # ... and my gradient sums are stored
+      if ev_e[1 - p] is not None:
+        main.wait_event(ev_e[1 - p])   # ... and I have read rows_in[1-p] (lookup t+1 rewrites it)
+      main.wait_event(ev_z)
+      self._barrier(1)             # B(t)
       ev_b = t.cuda.Event()
       ev_b.record(main)
-      self._owner_update()
+      ev_b_prev = ev_b
+      self._owner_update(p)
+      ev_apply[p] = t.cuda.Event()
+      ev_apply[p].record(main)
       with t.cuda.stream(s_e):
         s_e.wait_event(ev_b)
         ops.route_fill_peer(G, C, self.seg_ids[p], self.seg_occ[p], S["route"]["counts"])
-        ops.expand_rows(self.rows_in, S["route"]["perm"], S["idx"], B, out)
+        ops.expand_rows(self.rows_in[p], S["route"]["perm"], S["idx"], B, out)
         ev_e[p] = t.cuda.Event()
         ev_e[p].record(s_e)
-        ev_e_prev = ev_e[p]
-    for s in (s_r, s_g, s_e):
+    for s in (s_r, s_o, s_e, s_z, s_g):
       main.wait_stream(s)
     return out
 
