@@ -295,8 +295,9 @@ class PeerShardedStep(PaddedShardedStep):
 
   `run` is one step, strictly after the previous one.  `run_rotation` issues a list of steps
   with only their true dependencies (the requester-side dedup, routing and gradient sum of
-  step t+1 run under the owner phase of step t): two inboxes and two sets of requester-side
-  buffers alternate, everything else is ordered by the barriers."""
+  step t+1, barrier A(t+1) and the owner-side dedup(t+1) run under the owner phase of step t):
+  every exchange buffer and both dedup buffer sets exist twice and alternate, barriers A and B
+  use separate flag channels, everything else is ordered by events and the barriers."""
 
   def __init__(self, *a, **kw):
     super().__init__(*a, **kw)
