@@ -430,7 +430,7 @@ def main_ours(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full
 # captures of round 1 (profiles/r01_ncu_kernels.txt); None where no capture exists
 STAGE_LAUNCHES = {"gather": 1, "unique": 3, "segment_sum": 2, "apply": 1, "step": 1}
-TRAFFIC = {"apply": 31.36e6, "gather": 8.33e6, "segment_sum": 22.23e6, "unique": 4.3e6}
+TRAFFIC = {"apply": 31.52e6, "gather": 8.33e6, "segment_sum": 22.23e6, "unique": 4.3e6}
 
 
 class LocalStepper:

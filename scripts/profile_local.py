@@ -17,15 +17,22 @@ st.prepare([torch.from_numpy(x).to(dev) for x in ids_np], [torch.from_numpy(x).t
 for i in range(20): st.step(i)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
+PIPE = os.environ.get("PIPE", "0") == "1" and st.rotation is not None
+if PIPE:
+  st.run_steps(bench.N_BATCHES)
+  torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-  for i in range(10): st.step(i)
+  if PIPE:
+    st.run_steps(bench.N_BATCHES)
+  else:
+    for i in range(10): st.step(i)
   torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "kv_trace_local.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
-per_step = max(1, len(ev) // 10)
-tail = ev[-2 * per_step:]
+per_step = max(1, len(ev) // (bench.N_BATCHES if PIPE else 10))
+tail = ev[-(4 if PIPE else 2) * per_step:]
 t0 = tail[0]["ts"]
 print("timeline (last 2 steps, %d kernels per step):" % per_step)
 for e in tail:
