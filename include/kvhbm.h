@@ -91,6 +91,12 @@ int kv_map_size(kv_table* t, kv_stream stream, int64_t* out);
  * time()/86400 truncated to 16 bits (kernels/utility.cc:38-40), injected. */
 int kv_gather_or_insert(kv_table* t, const int64_t* d_ids, const int32_t* d_counts,
                         int64_t n, float* d_out, uint16_t today, kv_stream stream);
+/* kv_gather_or_insert over the first min(n, *d_n) ids: the count comes from a kernel earlier on
+ * the stream (kv_unique's d_num_unique), as in embedding_lookup's unique -> gather
+ * (python/ops/embedding_ops.py:365-372), without a host round trip.  Rows past the count are
+ * left untouched. */
+int kv_gather_or_insert_n(kv_table* t, const int64_t* d_ids, const int32_t* d_counts, int64_t n,
+                          const int32_t* d_n, float* d_out, uint16_t today, kv_stream stream);
 /* KvVariableGatherOrZerosOp, kernels/kv_variable_ops.cc:348-429 ->
  * KvVariable::FindOrZeros kernels/kv_variable.h:239-254. */
 int kv_gather_or_zeros(kv_table* t, const int64_t* d_ids, int64_t n, float* d_out,

@@ -312,6 +312,22 @@ def test_group_adam_dev_advances_beta_powers_in_the_same_launch(batch):
   slot.check_state(rtol=RTOL, atol=ATOL)
 
 
+def test_lookup_reads_count_from_device():
+  # unique -> gather chain without a host read of the unique count (kv_gather_or_insert_n)
+  dim = 16
+  p = Pair(dim, enter_threshold=3)
+  ids = np.arange(100, 1100, dtype=np.int64)
+  counts = np.random.default_rng(4).integers(1, 5, size=ids.size).astype(np.int32)
+  n_dev = torch.tensor([700], dtype=torch.int32, device=DEV)
+  out = torch.full((ids.size, dim), 9.0, device=DEV)
+  ops.kv_variable_gather_or_insert_with_counts(p.gpu, t(ids), t(counts), out=out, num_indices=n_dev)
+  want = p.cpu.gather_or_insert(ids[:700], counts[:700], today=TODAY)
+  got = out.cpu().numpy()
+  np.testing.assert_array_equal(got[:700], want.reshape(700, dim))
+  assert (got[700:] == 9.0).all()                   # rows past the count are left alone
+  p.check_state()                                   # and their keys were not inserted / counted
+
+
 def test_apply_reads_count_from_device():
   dim = 16
   var = Pair(dim)

@@ -35,6 +35,7 @@ SIGNATURES = {
     "kv_sum_freq": [vp, vp, C.POINTER(i64)],
     "kv_map_size": [vp, vp, C.POINTER(i64)],
     "kv_gather_or_insert": [vp, vp, vp, i64, vp, u16, vp],
+    "kv_gather_or_insert_n": [vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_gather_or_zeros": [vp, vp, i64, vp, vp],
     "kv_insert_or_update": [vp, vp, vp, i64, vp, vp, vp],
     "kv_scatter": [vp, i32, vp, vp, i64, vp],

@@ -13,7 +13,7 @@ Workspace* workspace_new();
 void workspace_delete(Workspace*);
 
 int do_gather(Table*, bool insert, const int64_t*, const int32_t*, int64_t, float*, uint16_t,
-              cudaStream_t);
+              cudaStream_t, const int32_t* d_n = nullptr);
 int do_scatter(Table*, int op, const int64_t*, const float*, int64_t, cudaStream_t);
 int do_insert(Table*, const int64_t*, const float*, int64_t, const uint8_t*, const uint8_t*,
               cudaStream_t);
@@ -196,6 +196,12 @@ int kv_gather_or_insert(kv_table* t, const int64_t* d_ids, const int32_t* d_coun
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_insert: bad arguments");
   return do_gather(&t->t, true, d_ids, d_counts, n, d_out, today, S(stream));
+}
+int kv_gather_or_insert_n(kv_table* t, const int64_t* d_ids, const int32_t* d_counts, int64_t n,
+                          const int32_t* d_n, float* d_out, uint16_t today, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_insert_n: bad arguments");
+  return do_gather(&t->t, true, d_ids, d_counts, n, d_out, today, S(stream), d_n);
 }
 int kv_gather_or_zeros(kv_table* t, const int64_t* d_ids, int64_t n, float* d_out,
                        kv_stream stream) {

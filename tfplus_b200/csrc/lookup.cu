@@ -63,7 +63,8 @@ template <int VEC, int CPL, bool INSERT, int UQ, bool SEG>
 __global__ void __launch_bounds__(256)
 gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
               long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags,
-              float* const* __restrict__ seg_out, int seg_len) {
+              float* const* __restrict__ seg_out, int seg_len, const int* __restrict__ d_n) {
+  if (d_n) { const long long dn = *d_n; if (dn < n) n = dn; }  // count produced on the device
   // A warp takes `kpw` ids (lanes < kpw probe): small kpw = more warps, so the machine is
   // full even for a 64 K-id batch and instruction latency hides behind other warps.
   constexpr int UNR = UQ / CPL > 0 ? UQ / CPL : 1;  // rows in flight per lane
@@ -750,9 +751,9 @@ __global__ void scatter_rows_n_kernel(const float* __restrict__ src, const int* 
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
                   float* out, uint16_t today, cudaStream_t st, int tpr,
-                  float* const* seg_out = nullptr, int seg_len = 0) {
+                  float* const* seg_out = nullptr, int seg_len = 0, const int32_t* d_n = nullptr) {
   static const int use_bulk = getenv("KVHBM_GATHER_BULK") ? atoi(getenv("KVHBM_GATHER_BULK")) : 0;
-  if (use_bulk && !seg_out && VEC == 4 && tb->dim * 4 <= 1024) {
+  if (use_bulk && !seg_out && !d_n && VEC == 4 && tb->dim * 4 <= 1024) {
     // 4 warps x 32 rows of staging per block
     const int kpi = 32 / tpr;
     int kpw = 32;
@@ -791,10 +792,10 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
   const long long warps = (n + kpw - 1) / kpw;
   const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const long long* k = reinterpret_cast<const long long*>(ids);
-#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0)
+#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0, d_n)
   if (seg_out) {
     gather_kernel<VEC, CPL, true, 8, true><<<blocks, bs, 0, st>>>(
-        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len);
+        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len, d_n);
   } else if (insert) { if (uq == 4) KV_G(true, 4); else if (uq == 8) KV_G(true, 8); else KV_G(true, 16); }
   else { if (uq == 4) KV_G(false, 4); else if (uq == 8) KV_G(false, 8); else KV_G(false, 16); }
 #undef KV_G
@@ -850,11 +851,11 @@ int launch_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
   } while (0)
 
 int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
-              float* out, uint16_t today, cudaStream_t st) {
+              float* out, uint16_t today, cudaStream_t st, const int32_t* d_n) {
   if (n <= 0) return 0;
   if (insert) KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
-#define CALL(V, C) launch_gather<V, C>(tb, insert, ids, counts, n, out, today, st, g.tpr)
+#define CALL(V, C) launch_gather<V, C>(tb, insert, ids, counts, n, out, today, st, g.tpr, nullptr, 0, d_n)
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL
 }

@@ -249,8 +249,11 @@ def kv_variable_gather_or_insert_v2(table_handle, indices, out=None):
   return kv_variable_gather_or_insert_with_counts(table_handle, indices, None, out=out)
 
 
-def kv_variable_gather_or_insert_with_counts(table_handle, indices, counts, out=None):
-  """Op `KvVariableGatherOrInsertWithCounts` (ops/kv_variable_ops.cc:322-332)."""
+def kv_variable_gather_or_insert_with_counts(table_handle, indices, counts, out=None,
+                                             num_indices=None):
+  """Op `KvVariableGatherOrInsertWithCounts` (ops/kv_variable_ops.cc:322-332).  num_indices: an
+  int32 device scalar; only the first min(len, num_indices) ids are looked up (rows past it are
+  left as they are) — the unique -> gather chain without a host read of the unique count."""
   h = table_handle
   ids = _ids(indices, h)
   if counts is not None:
@@ -266,7 +269,10 @@ def kv_variable_gather_or_insert_with_counts(table_handle, indices, counts, out=
     counts = counts.to(h.device).contiguous()
   if out is None:
     out = torch.empty(tuple(ids.shape) + (h.dim,), dtype=torch.float32, device=h.device)
-  if ids.numel():
+  if ids.numel() and num_indices is not None:
+    check(h._lib.kv_gather_or_insert_n(h._live(), ids.data_ptr(), _ptr(counts), ids.numel(),
+                                       num_indices.data_ptr(), out.data_ptr(), today(), h.stream))
+  elif ids.numel():
     check(h._lib.kv_gather_or_insert(h._live(), ids.data_ptr(), _ptr(counts), ids.numel(),
                                      out.data_ptr(), today(), h.stream))
   return out
