@@ -437,9 +437,9 @@ class LocalStepper:
   """One GPU: var + m_v_linear tables and the four-stage step.
 
   The optimizer's scalar inputs live in device memory (`hp`, as TF would hand them to a GPU
-  kernel) and beta^t is advanced on the device after every apply (TF Adam's `_finish`), so a
-  whole step is capturable: the timed loops replay one CUDA graph per rotating batch instead of
-  paying ~10 host launches per 30 us step.
+  kernel) and beta^t is advanced on the device by every apply launch (TF Adam's `_finish`), so
+  whole steps are capturable: the timed loops replay CUDA graphs (one per rotation of the
+  batches, or one per step) instead of paying ~10 host launches per step.
   """
 
   STAGES = ["gather", "unique", "segment_sum", "apply"]
@@ -457,7 +457,6 @@ class LocalStepper:
     self.hp = torch.tensor([HP["lr"], HP["beta1"], HP["beta2"], HP["beta1"], HP["beta2"],
                             HP["epsilon"], HP["l1"], HP["l2"], HP["l21"]], dtype=torch.float32,
                            device=dev)
-    self.betas = torch.tensor([HP["beta1"], HP["beta2"]], dtype=torch.float32, device=dev)
     self.graphs = {}
     self.overlap = os.environ.get("KVHBM_BENCH_OVERLAP", "1") != "0"
     self.side = torch.cuda.Stream(device=dev)
@@ -538,7 +537,7 @@ class LocalStepper:
     l0 = self.ops._lib.launch_count()
     for ids, grad, buf in zip(ids_d, grads_d, self.bufs):
       self.step_eager(ids, grad, buf)
-    # kernels of this library per step (+1: torch's in-place multiply that advances beta^t)
+    # kernels of this library per step (the beta^t advance is inside the apply launch)
     self.launches_per_step = (self.ops._lib.launch_count() - l0) // len(ids_d)
     self.torch.cuda.synchronize()
     # captured work may not grow the tables: make the room now (also refreshes the exact counts)
