@@ -82,3 +82,24 @@ def test_product_code_never_touches_the_oracle():
         text = open(os.path.join(dirpath, f)).read()
         assert "oracle" not in text.replace("oracle/kv_oracle.cc", "").replace(
             "see oracle", "") or f == "sharded.py", (dirpath, f)
+
+
+def test_argument_checks_need_no_gpu(lib):
+  """Null / out-of-range arguments are refused with InvalidArgument and a message before any
+  CUDA call, as the reference's OP_REQUIRES checks are (no device work happens here)."""
+  null = ctypes.c_void_p()
+  INVALID = 1
+  cases = [
+      ("kv_peer_barrier", (null, null, null, 0, 2, 1000, null), b"peer_barrier"),
+      ("kv_route_fill_peer", (4, 128, null, null, null, null), b"route_fill_peer"),
+      ("kv_unique_route_peer", (null, null, 0, null, null, null, null, 4, 0, 128, null, null,
+                                null, null, null, null), b"unique_route_peer"),
+      ("kv_route_ids_peer", (null, null, null, 0, null, 4, 0, 128, null, null, null, null, null,
+                             null), b"route_ids_peer"),
+      ("kv_route_id_pairs", (null, null, null, 0, null, 4, 0, 128, null, null, null, null, null),
+       b"route_id_pairs"),
+  ]
+  for name, args, needle in cases:
+    rc = getattr(lib, name)(*args)
+    assert rc == INVALID, (name, rc)
+    assert needle in lib.kv_last_error(), (name, lib.kv_last_error())
