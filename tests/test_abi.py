@@ -81,7 +81,7 @@ def test_product_code_never_touches_the_oracle():
       if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
         text = open(os.path.join(dirpath, f)).read()
         assert "oracle" not in text.replace("oracle/kv_oracle.cc", "").replace(
-            "see oracle", "") or f == "sharded.py", (dirpath, f)
+            "see oracle", ""), (dirpath, f)
 
 
 def test_argument_checks_need_no_gpu(lib):
