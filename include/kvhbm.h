@@ -177,7 +177,9 @@ int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids,
 /* The `_dev` apply plus AdamOptimizer._finish in the same launch: once every row is updated,
  * beta1_power *= beta1 and beta2_power *= beta2 inside d_hp (group_adam.py inherits _finish
  * from tf.train.AdamOptimizer; python/training/adam.py keeps the powers as non-slot variables),
- * so a training step needs no separate scalar-update op between two applies. */
+ * so a training step needs no separate scalar-update op between two applies.  The election of
+ * the last block uses a counter of the var table: launches on one var table must not overlap
+ * (they never do on one stream; callers using several streams order them with events). */
 int kv_apply_group_adam_v4_dev_advance(kv_table* var, kv_table* m_v_linear, const int64_t* d_ids,
                                        const float* d_grad, int64_t n, const int32_t* d_n,
                                        float* d_hp, uint16_t today, kv_stream stream);
