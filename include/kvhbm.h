@@ -187,6 +187,92 @@ int kv_apply_adam_dev_advance(kv_table* var, kv_table* m_v, const int64_t* d_ids
                               const float* d_grad, int64_t n, const int32_t* d_n, float* d_hp,
                               uint16_t today, kv_stream stream);
 
+/* ---- optimizer variants that share the fused apply ------------------------- */
+
+/* KvVariableGroupSparseApplyAdamV3Op, kernels/training_ops.cc:5710-5965: as V4 but lr divides
+ * the curvature terms instead of scaling alpha / l1 / l2 / l21 (:5846-5849, :5893-5925). */
+int kv_apply_group_adam_v3(kv_table* var, kv_table* m_v_linear, const int64_t* d_ids,
+                           const float* d_grad, int64_t n, const int32_t* d_n,
+                           float lr, float beta1_power, float beta2_power,
+                           float beta1, float beta2, float epsilon, float l1,
+                           float l2, float l21, uint16_t today, kv_stream stream);
+/* KvVariableSparseApplyFtrlV2 (KvVariableSparseApplyFtrlOp<has_l2_shrinkage=true>),
+ * kernels/training_ops.cc:281-530: FTRL-proximal per row, no group lasso, no blacklist. */
+int kv_apply_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* linear,
+                            const int64_t* d_ids, const float* d_grad, int64_t n,
+                            const int32_t* d_n, float lr, float l1, float l2,
+                            float l2_shrinkage, float lr_power, uint16_t today,
+                            kv_stream stream);
+/* KvVariableGroupSparseApplyFtrlV2, kernels/training_ops.cc:805-1062: group lasso on the
+ * norm of `linear` itself with threshold l1 (:976-1013). */
+int kv_apply_group_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* linear,
+                                  const int64_t* d_ids, const float* d_grad, int64_t n,
+                                  const int32_t* d_n, float lr, float l1, float l2,
+                                  float l2_shrinkage, float lr_power, uint16_t today,
+                                  kv_stream stream);
+
+/* ---- dedup plan: unique_with_counts + occurrence lists of one id batch -------
+ * What the hot path derives from the ids ALONE, built once per batch and handed to the
+ * lookup and to the fused segment-sum + apply of that batch:
+ *   - tf.unique_with_counts(ids): uniq (first-occurrence order), idx (int32 inverse),
+ *     counts, num_unique — the Unique that embedding_lookup_sparse places before the
+ *     gather (python/ops/embedding_ops.py:365-372) and that TF's
+ *     Optimizer._deduplicate_indexed_slices places before the apply
+ *     (python/ops/variable_scope.py:1096-1106);
+ *   - the occurrences of every distinct id in increasing position (seg_off / pos, a CSR),
+ *     which is what lets UnsortedSegmentSum run in TF's order without atomics.
+ * It depends on nothing but the ids, so an input pipeline can build the plan of batch t+1
+ * while batch t trains.  A plan holds up to `max_ids` ids; buffers are allocated once. */
+typedef struct kv_plan kv_plan;
+int kv_plan_create(int64_t max_ids, kv_plan** out);
+int kv_plan_destroy(kv_plan* plan);
+int kv_plan_build(kv_plan* plan, kv_workspace* ws, const int64_t* d_ids, int64_t n,
+                  kv_stream stream);
+/* Device pointers of the plan's arrays (any may be NULL): uniq[n], idx[n], counts[n],
+ * num_unique[1], seg_off[n], pos[n]; valid until the plan is destroyed, contents until the
+ * next build. */
+int kv_plan_arrays(const kv_plan* plan, const int64_t** d_uniq, const int32_t** d_idx,
+                   const int32_t** d_counts, const int32_t** d_num_unique,
+                   const int32_t** d_seg_off, const int32_t** d_pos);
+/* KvVariableGatherOrInsertV2 over the batch the plan was built from: d_out[n, dim].  Every
+ * distinct id is found-or-inserted ONCE with its occurrence count (the reference's own
+ * unique -> KvVariableGatherOrInsertWithCounts -> gather chain, embedding_ops.py:365-441), then
+ * rows are expanded to all positions; table state and output equal kv_gather_or_insert on the
+ * raw ids.  Leaves the slot of every distinct id in the plan for kv_apply_plan. */
+int kv_gather_or_insert_plan(kv_table* t, kv_plan* plan, float* d_out, uint16_t today,
+                             kv_stream stream);
+int kv_gather_or_zeros_plan(kv_table* t, kv_plan* plan, float* d_out, kv_stream stream);
+/* tf.math.unsorted_segment_sum(d_data[n, dim], plan.idx, num_unique) into d_out[num_unique, dim],
+ * every segment summed in increasing position from +0 (TF's CPU order): deterministic. */
+int kv_segment_sum_plan(kv_plan* plan, const float* d_data, int dim, float* d_out,
+                        kv_stream stream);
+
+typedef enum {
+  KV_OPT_ADAGRAD = 0,              /* hp = [lr] */
+  KV_OPT_GROUP_ADAM_V4 = 1,        /* [lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21] */
+  KV_OPT_SPARSE_GROUP_FTRL = 2,    /* [lr, l1, l2, l21, l2_shrinkage, lr_power] */
+  KV_OPT_ADAM = 3,                 /* [lr, beta1, beta2, epsilon, beta1_power, beta2_power] */
+  KV_OPT_GROUP_ADAM_V3 = 4,        /* as V4 */
+  KV_OPT_SPARSE_FTRL_V2 = 5,       /* [lr, l1, l2, 0, l2_shrinkage, lr_power] */
+  KV_OPT_GROUP_SPARSE_FTRL_V2 = 6  /* [lr, l1, l2, 0, l2_shrinkage, lr_power] */
+} kv_optimizer;
+/* UnsortedSegmentSum + KvVariable*Apply* of optimizer `kind` in ONE launch:
+ * d_grad[n, dim] holds one gradient row per id OCCURRENCE of the plan's batch (the
+ * IndexedSlices values as the backward pass produces them); the duplicate rows of an id are
+ * summed in TF's order inside the kernel that updates the id's rows.  Equivalent to
+ * kv_unique + kv_segment_sum + kv_apply_<kind>; this is what an optimizer's
+ * _apply_sparse_duplicate_indices override calls.  slot_b is NULL unless the optimizer has
+ * two slot tables (the FTRL family: slot_a = accum, slot_b = linear).  hp = the op's scalar
+ * inputs in op order (n_hp of them, see kv_optimizer). */
+int kv_apply_plan(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_b, kv_plan* plan,
+                  const float* d_grad, const float* hp, int n_hp, int update_slots,
+                  uint16_t today, kv_stream stream);
+/* Same with the scalar inputs in device memory (CUDA-graph capturable); advance_powers != 0
+ * also performs AdamOptimizer._finish (beta^t *= beta) inside d_hp once every row is updated. */
+int kv_apply_plan_dev(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_b,
+                      kv_plan* plan, const float* d_grad, float* d_hp, int advance_powers,
+                      int update_slots, uint16_t today, kv_stream stream);
+
 /* ---- dedup (stock TF ops on the path; TF 2.13 Unique / UnsortedSegmentSum) */
 
 int kv_workspace_create(kv_workspace** out);

@@ -694,6 +694,49 @@ void kvo_apply_adagrad(void* hvar, void* hacc, const int64_t* ids,
   });
 }
 
+// `l1_linear.square().sum()` (training_ops.cc:7180, :737) is an Eigen::Tensor full
+// reduction.  Eigen is NOT in /root/reference: TF 2.13.0 pins it in
+// third_party/eigen3/workspace.bzl and the reference is compiled against TF's headers
+// with no -march flag (kv_variable/BUILD:71-76,118-122), i.e. SSE2, Packet4f, no FMA.
+// Restated from unsupported/Eigen/CXX11/src/Tensor/TensorReduction.h,
+// InnerMostDimReducer<Self, SumReducer<float>, /*Vectorizable=*/true, /*Tree=*/true>::reduce:
+// up to 4 * 1024 coefficients it forwards to the <true, false> specialisation, which
+//   * runs four packet accumulators over the first (n / 16) * 16 coefficients
+//     (packet P goes to accumulator P % 4), then folds them ((p0 + p1) + p2) + p3,
+//   * adds the remaining whole packets to p0 one by one,
+//   * sums the scalar tail (n % 4 coefficients) sequentially from 0,
+//   * returns  tail + predux(p0),  predux<Packet4f> = (p0[0] + p0[2]) + (p0[1] + p0[3])
+//     (Eigen/src/Core/arch/SSE/PacketMath.h, the movehl/add_ss form).
+// The device kernel (tfplus_b200/csrc/apply_math.cuh, eigen_sum_tile) restates the same
+// order, so the group-lasso norm agrees bit for bit.  PARITY UNPINNED against the real
+// Eigen build (it cannot be compiled here).
+static float EigenSumSquares(const float* z, int n) {
+  if (n > 4 * 1024) {  // tree reduction: split at a packet boundary (TensorReduction.h)
+    const int split = 4 * (((n + 1) / 2 + 3) / 4);
+    float acc = 0.f;
+    acc += EigenSumSquares(z, split);
+    if (split < n) acc += EigenSumSquares(z + split, n - split);
+    return acc;
+  }
+  const int npk = n / 4;
+  const int n4 = (npk / 4) * 4;
+  float p[4][4] = {{0.f}};
+  for (int P = 0; P < n4; ++P)
+    for (int m = 0; m < 4; ++m) p[P & 3][m] += z[P * 4 + m] * z[P * 4 + m];
+  if (n4 > 0)
+    for (int m = 0; m < 4; ++m) {
+      p[0][m] = p[0][m] + p[1][m];
+      p[0][m] = p[0][m] + p[2][m];
+      p[0][m] = p[0][m] + p[3][m];
+    }
+  for (int P = n4; P < npk; ++P)
+    for (int m = 0; m < 4; ++m) p[0][m] += z[P * 4 + m] * z[P * 4 + m];
+  float tail = 0.f;
+  for (int e = npk * 4; e < n; ++e) tail += z[e] * z[e];
+  const float pr = (p[0][0] + p[0][2]) + (p[0][1] + p[0][3]);
+  return tail + pr;
+}
+
 // KvVariableGroupSparseApplyAdamV4Op, training_ops.cc:7105-7203.
 void kvo_apply_group_adam_v4(void* hvar, void* hmvl, const int64_t* ids,
                              const float* grad, int64_t n, float lr,
@@ -722,7 +765,6 @@ void kvo_apply_group_adam_v4(void* hvar, void* hmvl, const int64_t* ids,
       float* v = o + D;
       float* lin = o + 2 * D;
       const float* g = grad + i * D;
-      float ss = 0.f;
       for (int j = 0; j < D; ++j) {
         m[j] = beta1 * m[j] + (1.0f - beta1) * g[j];
         const float nv = beta2 * v[j] + (1.0f - beta2) * (g[j] * g[j]);
@@ -734,9 +776,8 @@ void kvo_apply_group_adam_v4(void* hvar, void* hmvl, const int64_t* ids,
           lin[j] += alpha * m[j] - (s_nv + epsilon) * w[j];
         const float adj = MaxF(MinF(lin[j], l1s), -l1s);
         z[j] = adj - lin[j];
-        ss += z[j] * z[j];
       }
-      const float nrm = std::sqrt(ss);
+      const float nrm = std::sqrt(EigenSumSquares(z.data(), D));
       if (nrm > l21_norm) {
         const float c = 1.0f - l21_norm / nrm;
         for (int j = 0; j < D; ++j) {
@@ -784,7 +825,6 @@ void kvo_apply_sparse_group_ftrl(void* hvar, void* hacc, void* hlin,
       float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
       float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
       const float* g = grad + i * D;
-      float ss = 0.f;
       for (int j = 0; j < D; ++j) {
         gs[j] = g[j] + (2.0f * l2_shrinkage) * w[j];
         const float na = a[j] + gs[j] * gs[j];
@@ -792,9 +832,8 @@ void kvo_apply_sparse_group_ftrl(void* hvar, void* hacc, void* hlin,
         lin[j] += gs[j] - (pna[j] - P(a[j])) / lr * w[j];
         const float adj = MaxF(MinF(lin[j], l1), -l1);
         z[j] = adj - lin[j];
-        ss += z[j] * z[j];
       }
-      const float nrm = std::sqrt(ss);
+      const float nrm = std::sqrt(EigenSumSquares(z.data(), D));
       bool blacklisted = false;
       if (nrm > l21_norm) {
         const float c = 1.0f - (l21_norm / nrm);

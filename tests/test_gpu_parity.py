@@ -14,11 +14,11 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-6   # north-star: optimizer-updated values and slots within 1e-6 relative
 ATOL = 1e-7
-# Group lasso with a strong l21: var = z * (1 - tau/||z||) / y.  The GPU sums ||z||^2 in a
-# different order than the oracle (and than Eigen), a <= 1 ulp difference in the norm that
-# the cancellation in 1 - tau/||z|| amplifies by ||z|| / (||z|| - tau) for rows just above
-# the threshold.  Those cases are compared at 5e-5; everything else at 1e-6.
-RTOL_STRONG_L21 = 5e-5
+# Group lasso with a strong l21: var = z * (1 - tau/||z||) / y amplifies any difference in
+# ||z|| by ||z|| / (||z|| - tau) for rows just above the threshold.  Kernel and oracle both
+# restate the order in which Eigen's packet reduction adds ||z||^2 (apply_math.cuh
+# eigen_sum_tile, kv_oracle.cc EigenSumSquares), so these cases hold the same 1e-6.
+RTOL_STRONG_L21 = RTOL
 
 
 @pytest.fixture(autouse=True)
@@ -191,7 +191,7 @@ def test_group_adam_blacklist_and_revive():
     ids = rng.permutation(500)[:300].astype(np.int64)
     scale = 10.0 if step % 2 else 0.01
     g = (rng.normal(size=(300, dim)) * scale).astype(np.float32)
-    var.gather_or_insert(ids, exact=False)   # rows carry the 5e-5 tolerance of earlier steps
+    var.gather_or_insert(ids, exact=False)   # rows carry the tolerance of earlier steps
     ops.kv_variable_group_sparse_apply_adam_v4(var.gpu, slot.gpu, t(g), t(ids), 0.05, b1p, b2p, 0.9,
                                                0.999, 1e-8, 0.0, 0.0, 0.5)
     ob.apply_group_adam_v4(var.cpu, slot.cpu, ids, g, 0.05, b1p, b2p, 0.9, 0.999, 1e-8, 0.0, 0.0,

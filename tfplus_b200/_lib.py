@@ -51,6 +51,18 @@ SIGNATURES = {
     "kv_apply_adam_dev": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_apply_group_adam_v4_dev_advance": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
     "kv_apply_adam_dev_advance": [vp, vp, vp, vp, i64, vp, vp, u16, vp],
+    "kv_apply_group_adam_v3": [vp, vp, vp, vp, i64, vp] + [f32] * 9 + [u16, vp],
+    "kv_apply_sparse_ftrl_v2": [vp, vp, vp, vp, vp, i64, vp] + [f32] * 5 + [u16, vp],
+    "kv_apply_group_sparse_ftrl_v2": [vp, vp, vp, vp, vp, i64, vp] + [f32] * 5 + [u16, vp],
+    "kv_plan_create": [i64, C.POINTER(vp)],
+    "kv_plan_destroy": [vp],
+    "kv_plan_build": [vp, vp, vp, i64, vp],
+    "kv_plan_arrays": [vp] + [C.POINTER(vp)] * 6,
+    "kv_gather_or_insert_plan": [vp, vp, vp, u16, vp],
+    "kv_gather_or_zeros_plan": [vp, vp, vp, vp],
+    "kv_segment_sum_plan": [vp, vp, i32, vp, vp],
+    "kv_apply_plan": [i32, vp, vp, vp, vp, vp, C.POINTER(f32), i32, i32, u16, vp],
+    "kv_apply_plan_dev": [i32, vp, vp, vp, vp, vp, vp, i32, i32, u16, vp],
     "kv_workspace_create": [C.POINTER(vp)],
     "kv_workspace_destroy": [vp],
     "kv_unique": [vp, vp, i64, vp, vp, vp, vp, vp],

@@ -7,8 +7,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkvhbm.so")
-SOURCES = ["table.cu", "lookup.cu", "apply.cu", "dedup.cu", "ckpt.cu", "peer.cu", "capi.cu"]
-HEADERS = ["common.cuh", "table.h", os.path.join("..", "..", "include", "kvhbm.h")]
+SOURCES = ["table.cu", "lookup.cu", "apply.cu", "apply_plan.cu", "dedup.cu", "ckpt.cu", "peer.cu",
+           "capi.cu"]
+HEADERS = ["common.cuh", "table.h", "plan.h", "apply_math.cuh", "async_copy.cuh",
+           os.path.join("..", "..", "include", "kvhbm.h")]
 
 # -fmad=false: the reference's CPU build has no FMA contraction (configure.sh:136)
 # and optimizer parity is stated in ulps of separately rounded fp32 ops.

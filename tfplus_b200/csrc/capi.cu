@@ -3,10 +3,23 @@
 
 #include <string>
 
+#include "plan.h"
 #include "table.h"
 
 namespace kvhbm {
 struct Workspace;
+struct Plan;
+Plan* plan_new(int64_t max_ids, int heavy_t, int* rc);
+void plan_delete(Plan*);
+PlanView plan_view(const Plan*);
+int do_plan_build(Plan*, Workspace*, const int64_t*, int64_t, cudaStream_t);
+int do_gather_plan(Table*, bool insert, const PlanView&, const int*, float*, uint16_t, cudaStream_t);
+int do_apply(int kind, Table*, Table*, Table*, const int64_t*, const float*, int64_t,
+             const int32_t*, const float* hp, const float* d_hp, int update_slots, uint16_t,
+             cudaStream_t, float* d_adv);
+int do_apply_plan(int kind, Table*, Table*, Table*, Plan*, const float*, const float* hp,
+                  const float* d_hp, int update_slots, uint16_t, cudaStream_t, float* d_adv);
+int do_segment_sum_plan(Plan*, const float*, int, float*, cudaStream_t);
 const std::string& last_error();
 long long launch_count();
 Workspace* workspace_new();
@@ -92,6 +105,7 @@ using namespace kvhbm;
 
 struct kv_table { Table t; };
 struct kv_workspace { Workspace* w; };
+struct kv_plan { Plan* p; };
 
 namespace {
 inline cudaStream_t S(kv_stream s) { return static_cast<cudaStream_t>(s); }
@@ -350,6 +364,129 @@ int kv_apply_adam_dev_advance(kv_table* var, kv_table* m_v, const int64_t* d_ids
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream),
                        d_hp);
+}
+
+// ---- optimizer variants sharing the apply template ----
+int kv_apply_group_adam_v3(kv_table* var, kv_table* mvl, const int64_t* d_ids,
+                           const float* d_grad, int64_t n, const int32_t* d_n, float lr,
+                           float beta1_power, float beta2_power, float beta1, float beta2,
+                           float epsilon, float l1, float l2, float l21, uint16_t today,
+                           kv_stream stream) {
+  MultiGuard g(var, mvl, nullptr);
+  if (g.rc) return g.rc;
+  const float hp[9] = {lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21};
+  return do_apply(KV_OPT_GROUP_ADAM_V3, &var->t, &mvl->t, nullptr, d_ids, d_grad, n, d_n, hp,
+                  nullptr, 1, today, S(stream), nullptr);
+}
+int kv_apply_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* linear,
+                            const int64_t* d_ids, const float* d_grad, int64_t n,
+                            const int32_t* d_n, float lr, float l1, float l2, float l2_shrinkage,
+                            float lr_power, uint16_t today, kv_stream stream) {
+  MultiGuard g(var, accum, linear);
+  if (g.rc) return g.rc;
+  const float hp[6] = {lr, l1, l2, 0.f, l2_shrinkage, lr_power};
+  return do_apply(KV_OPT_SPARSE_FTRL_V2, &var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, hp,
+                  nullptr, 1, today, S(stream), nullptr);
+}
+int kv_apply_group_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* linear,
+                                  const int64_t* d_ids, const float* d_grad, int64_t n,
+                                  const int32_t* d_n, float lr, float l1, float l2,
+                                  float l2_shrinkage, float lr_power, uint16_t today,
+                                  kv_stream stream) {
+  MultiGuard g(var, accum, linear);
+  if (g.rc) return g.rc;
+  const float hp[6] = {lr, l1, l2, 0.f, l2_shrinkage, lr_power};
+  return do_apply(KV_OPT_GROUP_SPARSE_FTRL_V2, &var->t, &accum->t, &linear->t, d_ids, d_grad, n,
+                  d_n, hp, nullptr, 1, today, S(stream), nullptr);
+}
+
+// ---- dedup plan ----
+int kv_plan_create(int64_t max_ids, kv_plan** out) {
+  KV_NEED(out != nullptr, "kv_plan_create: out is null");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KV_INTERNAL, "kvhbm needs a CUDA device: there is no CPU fallback");
+  }
+  int rc = 0;
+  Plan* p = plan_new(max_ids, 0, &rc);
+  if (!p) return rc;
+  kv_plan* h = new kv_plan();
+  h->p = p;
+  *out = h;
+  return KV_OK;
+}
+int kv_plan_destroy(kv_plan* plan) {
+  if (!plan) return KV_OK;
+  cudaDeviceSynchronize();
+  plan_delete(plan->p);
+  delete plan;
+  return KV_OK;
+}
+int kv_plan_build(kv_plan* plan, kv_workspace* ws, const int64_t* d_ids, int64_t n,
+                  kv_stream stream) {
+  KV_NEED(plan && ws && (n == 0 || d_ids), "plan_build: bad arguments");
+  return do_plan_build(plan->p, ws->w, d_ids, n, S(stream));
+}
+int kv_plan_arrays(const kv_plan* plan, const int64_t** d_uniq, const int32_t** d_idx,
+                   const int32_t** d_counts, const int32_t** d_num_unique,
+                   const int32_t** d_seg_off, const int32_t** d_pos) {
+  KV_NEED(plan != nullptr, "plan_arrays: null plan");
+  const PlanView v = plan_view(plan->p);
+  if (d_uniq) *d_uniq = reinterpret_cast<const int64_t*>(v.uniq);
+  if (d_idx) *d_idx = v.idx;
+  if (d_counts) *d_counts = v.counts;
+  if (d_num_unique) *d_num_unique = v.num;
+  if (d_seg_off) *d_seg_off = v.seg_off;
+  if (d_pos) *d_pos = v.pos;
+  return KV_OK;
+}
+int kv_gather_or_insert_plan(kv_table* t, kv_plan* plan, float* d_out, uint16_t today,
+                             kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(plan && d_out, "gather_or_insert_plan: bad arguments");
+  const PlanView v = plan_view(plan->p);
+  return do_gather_plan(&t->t, true, v, v.first, d_out, today, S(stream));
+}
+int kv_gather_or_zeros_plan(kv_table* t, kv_plan* plan, float* d_out, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(plan && d_out, "gather_or_zeros_plan: bad arguments");
+  const PlanView v = plan_view(plan->p);
+  return do_gather_plan(&t->t, false, v, v.first, d_out, 0, S(stream));
+}
+int kv_segment_sum_plan(kv_plan* plan, const float* d_data, int dim, float* d_out,
+                        kv_stream stream) {
+  KV_NEED(plan && d_data && d_out && dim > 0, "segment_sum_plan: bad arguments");
+  return do_segment_sum_plan(plan->p, d_data, dim, d_out, S(stream));
+}
+static int n_hp_of(int kind) {
+  switch (kind) {
+    case KV_OPT_ADAGRAD: return 1;
+    case KV_OPT_GROUP_ADAM_V4: case KV_OPT_GROUP_ADAM_V3: return 9;
+    case KV_OPT_SPARSE_GROUP_FTRL: case KV_OPT_SPARSE_FTRL_V2: case KV_OPT_GROUP_SPARSE_FTRL_V2:
+    case KV_OPT_ADAM: return 6;
+  }
+  return -1;
+}
+int kv_apply_plan(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_b, kv_plan* plan,
+                  const float* d_grad, const float* hp, int n_hp, int update_slots, uint16_t today,
+                  kv_stream stream) {
+  MultiGuard g(var, slot_a, slot_b);
+  if (g.rc) return g.rc;
+  KV_NEED(plan && hp, "apply_plan: bad arguments");
+  KV_NEED(n_hp_of(kind) == n_hp, "apply_plan: wrong number of scalar inputs for this optimizer");
+  return do_apply_plan(kind, &var->t, &slot_a->t, slot_b ? &slot_b->t : nullptr, plan->p, d_grad,
+                       hp, nullptr, update_slots, today, S(stream), nullptr);
+}
+int kv_apply_plan_dev(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_b, kv_plan* plan,
+                      const float* d_grad, float* d_hp, int advance_powers, int update_slots,
+                      uint16_t today, kv_stream stream) {
+  MultiGuard g(var, slot_a, slot_b);
+  if (g.rc) return g.rc;
+  KV_NEED(plan && d_hp && n_hp_of(kind) > 0, "apply_plan_dev: bad arguments");
+  return do_apply_plan(kind, &var->t, &slot_a->t, slot_b ? &slot_b->t : nullptr, plan->p, d_grad,
+                       nullptr, d_hp, update_slots, today, S(stream),
+                       advance_powers ? d_hp : nullptr);
 }
 
 int kv_workspace_create(kv_workspace** out) {

@@ -2,6 +2,9 @@
 // device and without sorting: Unique / UniqueWithCounts (first-occurrence
 // order, int32 inverse index), UnsortedSegmentSum, and the id routing used by
 // key-hash sharding.
+#include <cstdlib>
+
+#include "plan.h"
 #include "table.h"
 
 namespace kvhbm {
@@ -60,6 +63,24 @@ struct RouteOut {
   int num_shards, mode, cap;
 };
 
+// Extra outputs of the dedup when it builds a plan (kv_plan_build): the occurrences of every
+// distinct id as a CSR over positions — seg_off[r] = first entry of unique id r (exclusive
+// prefix of the counts in rank order), within[i] = entry of position i inside its segment (in
+// arrival order; plan_sort_* puts the segments into increasing position afterwards) — and the
+// list of "heavy" ids (more than heavy_t occurrences), which the fused apply sums on a
+// dedicated pipeline.
+struct PlanOut {
+  int* first;
+  uint2* hint;   // per rank, reset to "unknown" by every build
+  int* seg_off;
+  int* within;
+  int* pos_u;
+  int* heavy;
+  int* heavy_n;
+  int heavy_t;
+  int heavy_cap;
+};
+
 struct __align__(16) USlot {
   long long key;
   int first;  // smallest position holding this key; once ranked, ~rank (negative)
@@ -106,7 +127,8 @@ __global__ void unique_wipe_kernel(UScratch s) {
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
-                     int* __restrict__ slot_of) {
+                     int* __restrict__ slot_of, int* __restrict__ within, int* heavy_n) {
+  if (heavy_n && blockIdx.x == 0 && threadIdx.x == 0) *heavy_n = 0;
   USlot* tab = s.tab[s.sel[0] & 1];
   const unsigned long long mask = s.cap - 1;
   const int lane = threadIdx.x & 31;
@@ -121,6 +143,7 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
     const unsigned peers = __match_any_sync(active, key);
     const int leader = __ffs(peers) - 1;  // lowest lane = smallest position
     unsigned long long pos = 0;
+    int wbase = 0;
     if (lane == leader) {
       pos = mix64((unsigned long long)key) >> s.shift;
       for (;;) {
@@ -135,29 +158,44 @@ unique_insert_kernel(UScratch s, const long long* __restrict__ ids, long long n,
         pos = (pos + 1) & mask;
       }
       if (__ldcg(&tab[pos].first) > (int)i) atomicMin(&tab[pos].first, (int)i);
-      if (COUNT) atomicAdd(&tab[pos].count, __popc(peers));
+      if (COUNT) {
+        // the value the add returns places this warp's occurrences inside the id's segment
+        if (within) wbase = atomicAdd(&tab[pos].count, __popc(peers));
+        else atomicAdd(&tab[pos].count, __popc(peers));
+      }
     }
     pos = __shfl_sync(peers, pos, leader);
     slot_of[i] = (int)pos;
+    if (within) {
+      wbase = __shfl_sync(peers, wbase, leader);
+      within[i] = wbase + __popc(peers & ((1u << lane) - 1u));
+    }
   }
 }
 
 // Ranks of the first occurrences in position order, in one pass: every block of UB ids
 // counts its first occurrences, publishes the count, and obtains the number of first
 // occurrences before it by decoupled look-back over the earlier blocks' status words
-// (flag 1 = block aggregate, flag 2 = inclusive prefix; value in the low 32 bits).
+// (flag 1 = block aggregate, flag 2 = inclusive prefix, in bits 62-63; the word carries TWO
+// running sums: first occurrences in bits 0-30, and their occurrence counts in bits 31-61 —
+// the second is the exclusive prefix that becomes seg_off when a plan is built; both are
+// bounded by n <= 2^30).
 //
 // ROUTE: the same launch is the id exchange of the sharded step — a first occurrence is also
 // given a position in its owner's row (shared histogram, one global add per (block, shard))
 // and stored, with its occurrence count, straight into that row (peer memory).
-template <bool ROUTE>
+__device__ __forceinline__ unsigned long long st_pack(unsigned long long flag, int ranks,
+                                                      int occ) {
+  return (flag << 62) | ((unsigned long long)(unsigned)occ << 31) | (unsigned long long)(unsigned)ranks;
+}
+template <bool ROUTE, bool PLAN>
 __global__ void __launch_bounds__(256)
 unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
                    const long long* __restrict__ ids, long long n,
                    long long* __restrict__ uniq, int* __restrict__ counts,
-                   int* __restrict__ num_unique, RouteOut ro) {
-  __shared__ int warp_tot[8];
-  __shared__ int block_prefix;
+                   int* __restrict__ num_unique, RouteOut ro, PlanOut po) {
+  __shared__ int warp_tot[8], warp_occ[8];
+  __shared__ int block_prefix, block_occ;
   const int which = sc.sel[0] & 1;
   USlot* __restrict__ tab = sc.tab[which];
   unsigned long long* status = sc.status[which];
@@ -165,56 +203,71 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
   const long long base = blockIdx.x * (long long)UB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long i0 = base + threadIdx.x * 4;  // 4 consecutive positions per thread
-  int f[4], s[4];
-  int c = 0;
+  int f[4], s[4], cnt[4];
+  int c = 0, oc = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const long long i = i0 + k;
     s[k] = i < n ? slot_of[i] : 0;
-    f[k] = i < n ? (tab[s[k]].first == (int)i) : 0;
+    f[k] = 0;
+    cnt[k] = 0;
+    if (i < n) {
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(&tab[s[k]]));  // {key, first, count}
+      f[k] = v.z == (int)i;
+      cnt[k] = v.w;
+    }
     c += f[k];
+    if (PLAN) oc += f[k] ? cnt[k] : 0;
   }
-  int incl = c;
+  int incl = c, oincl = oc;
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
+    const int t2 = PLAN ? __shfl_up_sync(0xffffffffu, oincl, o) : 0;
+    if (lane >= o) { incl += t; oincl += t2; }
   }
-  if (lane == 31) warp_tot[warp] = incl;
+  if (lane == 31) { warp_tot[warp] = incl; warp_occ[warp] = oincl; }
   __syncthreads();
-  int woff = 0, total = 0;
+  int woff = 0, total = 0, wocc = 0, tocc = 0;
   for (int w = 0; w < 8; ++w) {
-    if (w < warp) woff += warp_tot[w];
+    if (w < warp) { woff += warp_tot[w]; wocc += warp_occ[w]; }
     total += warp_tot[w];
+    tocc += warp_occ[w];
   }
   if (warp == 0) {
     const int b = blockIdx.x;
     volatile unsigned long long* st = status;
-    if (lane == 0)
-      st[b] = ((b == 0 ? 2ULL : 1ULL) << 32) | (unsigned int)total;
-    int prefix = 0;
+    if (lane == 0) st[b] = st_pack(b == 0 ? 2ULL : 1ULL, total, tocc);
+    int prefix = 0, oprefix = 0;
     for (int j = b - 1; j >= 0; j -= 32) {
       const int idx = j - lane;
-      unsigned long long v = 2ULL << 32;  // lanes past block 0 act as a zero prefix
+      unsigned long long v = 2ULL << 62;  // lanes past block 0 act as a zero prefix
       if (idx >= 0) {
-        do { v = st[idx]; } while ((v >> 32) == 0);
+        do { v = st[idx]; } while ((v >> 62) == 0);
       }
-      const unsigned done = __ballot_sync(0xffffffffu, (v >> 32) == 2);
+      const unsigned done = __ballot_sync(0xffffffffu, (v >> 62) == 2);
       const int stop = done ? __ffs(done) - 1 : 32;  // nearest block that has its prefix
-      int add = lane <= stop ? (int)(v & 0xffffffffULL) : 0;
-      for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+      int add = lane <= stop ? (int)(v & 0x7fffffffULL) : 0;
+      int oadd = lane <= stop ? (int)((v >> 31) & 0x7fffffffULL) : 0;
+      for (int o = 16; o > 0; o >>= 1) {
+        add += __shfl_xor_sync(0xffffffffu, add, o);
+        oadd += __shfl_xor_sync(0xffffffffu, oadd, o);
+      }
       prefix += add;
+      oprefix += oadd;
       if (done) break;
     }
     if (lane == 0) {
-      if (b > 0) st[b] = (2ULL << 32) | (unsigned int)(prefix + total);
+      if (b > 0) st[b] = st_pack(2ULL, prefix + total, oprefix + tocc);
       block_prefix = prefix;
+      block_occ = oprefix;
       if (b == (int)gridDim.x - 1) *num_unique = prefix + total;
     }
   }
   __syncthreads();
   int r = block_prefix + woff + incl - c;
+  int off = block_occ + wocc + oincl - oc;
   long long key[4];
-  int cnt[4], rk[4];
+  int rk[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (f[k]) {
@@ -222,10 +275,18 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
       // overwriting first with the rank cannot turn any of them into a first occurrence
       key[k] = ids[i0 + k];
       uniq[r] = key[k];
-      cnt[k] = (counts || ROUTE) ? tab[s[k]].count : 1;
       if (counts) counts[r] = cnt[k];
       tab[s[k]].first = ~r;
       rk[k] = r;
+      if (PLAN) {
+        po.first[r] = (int)(i0 + k);
+        po.seg_off[r] = off;
+        if (cnt[k] > po.heavy_t) {
+          const int h = atomicAdd(po.heavy_n, 1);
+          if (h < po.heavy_cap) po.heavy[h] = r;
+        }
+        off += cnt[k];
+      }
       ++r;
     }
   }
@@ -263,20 +324,124 @@ unique_rank_kernel(UScratch sc, const int* __restrict__ slot_of,
   }
 }
 
-// idx[i] = rank of id i's slot; the same launch wipes the other table for the next call.
+// idx[i] = rank of id i's slot; with a plan also pos_u[seg_off[rank] + within[i]] = i (the
+// CSR of occurrences, segments still in arrival order); the same launch wipes the other table
+// for the next call.
 __global__ void unique_index_kernel(UScratch s, const int* __restrict__ slot_of, long long n,
-                                    int* __restrict__ idx) {
+                                    int* __restrict__ idx, PlanOut po) {
   const int which = s.sel[1] & 1;
   const USlot* __restrict__ tab = s.tab[which];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < n; j += stride) {
-    idx[j] = ~tab[slot_of[j]].first;
+    const int r = ~tab[slot_of[j]].first;
+    idx[j] = r;
+    if (po.pos_u) {
+      po.pos_u[po.seg_off[r] + po.within[j]] = (int)j;
+      po.hint[j] = make_uint2(0xffffffffu, 0u);  // (indexed by rank; ranks < n as well)
+    }
   }
   // NB: the table just used stays dirty until the call after next wipes it
   wipe(s.tab[which ^ 1], s.cap, s.status[which ^ 1], s.nb_max, (unsigned long long)i,
        (unsigned long long)stride);
   if (i == 0) s.sel[0] = which ^ 1;
+}
+
+// ---- plan: segments into increasing position ---------------------------------------------
+// Light segments (<= 32 occurrences): a warp loads the segment and every lane ranks its
+// position among the others (positions are distinct, so the ranks are a permutation).
+__global__ void __launch_bounds__(256)
+plan_sort_light_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
+                       const int* __restrict__ num_unique, const int* __restrict__ pos_u,
+                       int* __restrict__ pos, int heavy_t) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int U = *num_unique;
+  for (long long r0 = warp * 32; r0 < U; r0 += nwarps * 32) {
+    const long long r = r0 + lane;
+    const int c = r < U ? counts[r] : 0;
+    const int off = r < U ? seg_off[r] : 0;
+    if (c == 1) pos[off] = pos_u[off];
+    unsigned todo = __ballot_sync(0xffffffffu, c >= 2 && c <= heavy_t);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int cc = __shfl_sync(0xffffffffu, c, src);
+      const int oo = __shfl_sync(0xffffffffu, off, src);
+      for (int k0 = 0; k0 < cc; k0 += 32) {   // heavy_t may exceed 32: rank chunk by chunk
+        const int mine = k0 + lane < cc ? pos_u[oo + k0 + lane] : 0x7fffffff;
+        int rank = 0;
+        for (int q0 = 0; q0 < cc; q0 += 32) {
+          const int other = q0 == k0 ? mine : (q0 + lane < cc ? pos_u[oo + q0 + lane] : 0x7fffffff);
+          const int lim = cc - q0 < 32 ? cc - q0 : 32;
+          for (int j = 0; j < lim; ++j) rank += __shfl_sync(0xffffffffu, other, j) < mine;
+        }
+        if (k0 + lane < cc) pos[oo + rank] = mine;
+      }
+    }
+  }
+}
+
+// Heavy segments: a block per segment marks the segment's positions in a shared-memory bitmap
+// (one chunk of PLAN_CHUNK positions at a time) and writes the set bits back in order.
+constexpr int PLAN_CHUNK = 1 << 18;              // positions per bitmap chunk (32 KB of bits)
+constexpr int PLAN_WORDS = PLAN_CHUNK / 32;
+__global__ void __launch_bounds__(512)
+plan_sort_heavy_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
+                       const int* __restrict__ heavy, const int* __restrict__ heavy_n,
+                       int heavy_cap, const int* __restrict__ pos_u, int* __restrict__ pos,
+                       long long n) {
+  __shared__ unsigned bm[PLAN_WORDS];
+  __shared__ int wsum[16];
+  __shared__ int run_base;
+  int H = *heavy_n;
+  if (H > heavy_cap) H = heavy_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = blockIdx.x; h < H; h += gridDim.x) {
+    const int r = heavy[h];
+    const int c = counts[r], off = seg_off[r];
+    if (threadIdx.x == 0) run_base = 0;
+    for (long long c0 = 0; c0 < n; c0 += PLAN_CHUNK) {
+      const int words = (int)(((n - c0 < PLAN_CHUNK ? n - c0 : PLAN_CHUNK) + 31) >> 5);
+      for (int w = threadIdx.x; w < words; w += blockDim.x) bm[w] = 0u;
+      __syncthreads();
+      for (int e = threadIdx.x; e < c; e += blockDim.x) {
+        const long long p = pos_u[off + e] - c0;
+        if (p >= 0 && p < PLAN_CHUNK) atomicOr(&bm[p >> 5], 1u << (p & 31));
+      }
+      __syncthreads();
+      // every thread owns a contiguous range of words
+      const int per = (words + blockDim.x - 1) / blockDim.x;
+      const int w0 = threadIdx.x * per;
+      int mine = 0;
+      for (int w = w0; w < w0 + per && w < words; ++w) mine += __popc(bm[w]);
+      int incl = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      int before = run_base + incl - mine;
+      int total = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        if (w < warp) before += wsum[w];
+        total += wsum[w];
+      }
+      for (int w = w0; w < w0 + per && w < words; ++w) {
+        unsigned bits = bm[w];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          pos[off + before++] = (int)(c0 + (long long)w * 32 + b);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) run_base += total;
+      __syncthreads();
+    }
+  }
 }
 
 // ---- UnsortedSegmentSum ----------------------------------------------------
@@ -584,7 +749,8 @@ static bool ws_wiped(const Workspace* ws) { return ws->wiped_buf == ws->ubuf; }
 static void ws_mark_wiped(Workspace* ws) { ws->wiped_buf = ws->ubuf; }
 
 int do_unique_impl(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
-                   int32_t* counts, int32_t* num_unique, const RouteOut* route, cudaStream_t st) {
+                   int32_t* counts, int32_t* num_unique, const RouteOut* route, cudaStream_t st,
+                   const PlanOut* plan = nullptr) {
   if (n < 0 || n > (1LL << 30)) return fail(1, "unique: n out of range");
   if (n == 0) {
     KV_CUDA(cudaMemsetAsync(num_unique, 0, sizeof(int32_t), st));
@@ -634,18 +800,27 @@ int do_unique_impl(Workspace* ws, const int64_t* ids, int64_t n, int64_t* uniq, 
     KV_LAUNCHED();
     ws_mark_wiped(ws);
   }
-  if (counts || route) unique_insert_kernel<true><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
-  else unique_insert_kernel<false><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of);
-  KV_LAUNCHED();
-  if (route)
-    unique_rank_kernel<true><<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
-                                                 counts, num_unique, *route);
+  const PlanOut po = plan ? *plan : PlanOut{};
+  if (counts || route || plan)
+    unique_insert_kernel<true><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of, po.within,
+                                                                      po.heavy_n);
   else
-    unique_rank_kernel<false><<<nb, 256, 0, st>>>(sc, slot_of, k, n, reinterpret_cast<long long*>(uniq),
-                                                  counts, num_unique, RouteOut{});
+    unique_insert_kernel<false><<<blocks_for(n, 256, dev), 256, 0, st>>>(sc, k, n, slot_of, nullptr,
+                                                                       nullptr);
+  KV_LAUNCHED();
+  long long* uq = reinterpret_cast<long long*>(uniq);
+  if (route)
+    unique_rank_kernel<true, false><<<nb, 256, 0, st>>>(sc, slot_of, k, n, uq, counts, num_unique,
+                                                        *route, po);
+  else if (plan)
+    unique_rank_kernel<false, true><<<nb, 256, 0, st>>>(sc, slot_of, k, n, uq, counts, num_unique,
+                                                        RouteOut{}, po);
+  else
+    unique_rank_kernel<false, false><<<nb, 256, 0, st>>>(sc, slot_of, k, n, uq, counts, num_unique,
+                                                         RouteOut{}, po);
   KV_LAUNCHED();
   const long long span = n > (long long)sc.cap ? n : (long long)sc.cap;
-  unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx);
+  unique_index_kernel<<<blocks_for(span, 256, dev), 256, 0, st>>>(sc, slot_of, n, idx, po);
   KV_LAUNCHED();
   return 0;
 }
@@ -784,6 +959,130 @@ int do_unzip_pairs(const int64_t* pairs, int64_t n, int64_t* ids, int32_t* occ, 
   KV_CUDA(cudaGetDevice(&dev));
   unzip_pairs_kernel<<<blocks_for(n, 256, dev), 256, 0, st>>>(
       reinterpret_cast<const long long*>(pairs), n, reinterpret_cast<long long*>(ids), occ);
+  KV_LAUNCHED();
+  return 0;
+}
+
+// ---- dedup plan -------------------------------------------------------------------------------
+// Everything the hot path derives from the ids of one batch alone — tf.unique_with_counts plus
+// the CSR of occurrences — kept on the device for the lookup and the fused apply of that batch
+// (kvhbm.h kv_plan_*).  Depends on nothing but the ids, so it can be built ahead of the step.
+struct Plan {
+  int device = 0;
+  int64_t cap = 0;        // ids the buffers hold
+  int64_t n = 0;          // ids of the last build
+  int heavy_t = 32;
+  int heavy_cap = 0;
+  long long* uniq = nullptr;
+  int *idx = nullptr, *counts = nullptr, *num = nullptr, *seg_off = nullptr, *pos = nullptr;
+  int *pos_u = nullptr, *within = nullptr, *heavy = nullptr, *heavy_n = nullptr;
+  int* first = nullptr;
+  uint2* hint = nullptr;
+  // scratch of the fused apply's heavy path: gradient sums [heavy_cap][sum_dim], arrival counters
+  float* heavy_sum = nullptr;
+  int sum_dim = 0;
+  unsigned* heavy_done = nullptr;
+  void* block = nullptr;
+  ~Plan() {
+    if (block) cudaFree(block);
+    if (heavy_sum) cudaFree(heavy_sum);
+  }
+};
+
+__global__ void plan_clear_hints_kernel(uint2* hint, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) hint[i] = make_uint2(0xffffffffu, 0u);
+}
+// A new build invalidates what the previous batch's lookup left behind.
+int plan_forget_hints(Plan* p, cudaStream_t st) {
+  plan_clear_hints_kernel<<<blocks_for(p->cap, 256, p->device), 256, 0, st>>>(p->hint, p->cap);
+  KV_LAUNCHED();
+  return 0;
+}
+
+Plan* plan_new(int64_t max_ids, int heavy_t, int* rc) {
+  *rc = 0;
+  if (max_ids < 1 || max_ids > (1LL << 30)) { *rc = fail(1, "plan: max_ids must be in [1, 2^30]"); return nullptr; }
+  Plan* p = new Plan();
+  cudaGetDevice(&p->device);
+  p->cap = max_ids;
+  static const int ht_env = getenv("KVHBM_PLAN_HEAVY") ? atoi(getenv("KVHBM_PLAN_HEAVY")) : 0;
+  p->heavy_t = heavy_t > 0 ? heavy_t : (ht_env > 0 ? ht_env : 32);
+  p->heavy_cap = (int)(max_ids / (p->heavy_t + 1)) + 1;
+  const size_t a_i = align_up((size_t)max_ids * sizeof(int));
+  const size_t a_l = align_up((size_t)max_ids * sizeof(long long));
+  const size_t a_h = align_up((size_t)p->heavy_cap * sizeof(int));
+  const size_t total = 2 * a_l + 7 * a_i + 2 * a_h + 512;
+  cudaError_t e = cudaMalloc(&p->block, total);
+  if (e != cudaSuccess) { *rc = cuda_fail(e, "cudaMalloc(plan)"); delete p; return nullptr; }
+  cudaMemset(p->block, 0, total);
+  char* c = static_cast<char*>(p->block);
+  p->uniq = reinterpret_cast<long long*>(c); c += a_l;
+  p->idx = reinterpret_cast<int*>(c); c += a_i;
+  p->counts = reinterpret_cast<int*>(c); c += a_i;
+  p->seg_off = reinterpret_cast<int*>(c); c += a_i;
+  p->pos = reinterpret_cast<int*>(c); c += a_i;
+  p->pos_u = reinterpret_cast<int*>(c); c += a_i;
+  p->within = reinterpret_cast<int*>(c); c += a_i;
+  p->first = reinterpret_cast<int*>(c); c += a_i;
+  p->hint = reinterpret_cast<uint2*>(c); c += a_l;
+  p->heavy = reinterpret_cast<int*>(c); c += a_h;
+  p->heavy_done = reinterpret_cast<unsigned*>(c); c += a_h;
+  p->num = reinterpret_cast<int*>(c); c += 256;
+  p->heavy_n = reinterpret_cast<int*>(c);
+  plan_forget_hints(p, 0);
+  return p;
+}
+void plan_delete(Plan* p) { delete p; }
+
+PlanView plan_view(const Plan* p) {
+  PlanView v;
+  v.uniq = p->uniq; v.idx = p->idx; v.counts = p->counts; v.num = p->num;
+  v.seg_off = p->seg_off; v.pos = p->pos; v.heavy = p->heavy; v.heavy_n = p->heavy_n;
+  v.first = p->first; v.hint = p->hint; v.heavy_sum = p->heavy_sum; v.heavy_done = p->heavy_done;
+  v.heavy_t = p->heavy_t; v.heavy_cap = p->heavy_cap; v.sum_dim = p->sum_dim; v.n = p->n;
+  return v;
+}
+
+// The heavy path of the fused apply parks partial gradient sums here; sized on first use
+// (not during CUDA-graph capture: run the step once eagerly first).
+int plan_need_scratch(Plan* p, int dim, cudaStream_t st) {
+  const int want = (dim + 31) / 32 * 32;
+  if (p->heavy_sum && p->sum_dim >= want) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+  if (cs != cudaStreamCaptureStatusNone)
+    return fail(2, "plan: scratch must be sized before CUDA-graph capture (run once eagerly)");
+  KV_CUDA(cudaStreamSynchronize(st));
+  if (p->heavy_sum) cudaFree(p->heavy_sum);
+  p->heavy_sum = nullptr;
+  KV_CUDA(cudaMalloc(&p->heavy_sum, (size_t)p->heavy_cap * want * sizeof(float)));
+  p->sum_dim = want;
+  return 0;
+}
+
+int do_plan_build(Plan* p, Workspace* ws, const int64_t* ids, int64_t n, cudaStream_t st) {
+  if (n < 0 || n > p->cap) return fail(1, "plan_build: n exceeds the plan's capacity");
+  p->n = n;
+  PlanOut po;
+  po.first = p->first; po.hint = p->hint; po.seg_off = p->seg_off; po.within = p->within; po.pos_u = p->pos_u;
+  po.heavy = p->heavy; po.heavy_n = p->heavy_n; po.heavy_t = p->heavy_t; po.heavy_cap = p->heavy_cap;
+  if (n == 0) {
+    KV_CUDA(cudaMemsetAsync(p->num, 0, sizeof(int), st));
+    KV_CUDA(cudaMemsetAsync(p->heavy_n, 0, sizeof(int), st));
+    return 0;
+  }
+  KV_TRY(do_unique_impl(ws, ids, n, reinterpret_cast<int64_t*>(p->uniq), p->idx, p->counts, p->num,
+                        nullptr, st, &po));
+  const int dev = p->device;
+  // one warp per 32 distinct ids; U <= n
+  plan_sort_light_kernel<<<blocks_for((n + 31) / 32 * 32, 256, dev, 8), 256, 0, st>>>(
+      p->counts, p->seg_off, p->num, p->pos_u, p->pos, p->heavy_t);
+  KV_LAUNCHED();
+  int hb = p->heavy_cap < 2 * sm_count(dev) ? p->heavy_cap : 2 * sm_count(dev);
+  plan_sort_heavy_kernel<<<hb, 512, 0, st>>>(p->counts, p->seg_off, p->heavy, p->heavy_n,
+                                             p->heavy_cap, p->pos_u, p->pos, n);
   KV_LAUNCHED();
   return 0;
 }

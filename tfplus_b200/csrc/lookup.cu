@@ -8,6 +8,8 @@
 // issued before the first store.
 #include <cstdlib>
 
+#include "async_copy.cuh"
+#include "plan.h"
 #include "table.h"
 
 namespace kvhbm {
@@ -63,8 +65,13 @@ template <int VEC, int CPL, bool INSERT, int UQ, bool SEG>
 __global__ void __launch_bounds__(256)
 gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ counts,
               long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags,
-              float* const* __restrict__ seg_out, int seg_len, const int* __restrict__ d_n) {
+              float* const* __restrict__ seg_out, int seg_len, const int* __restrict__ d_n,
+              uint2* __restrict__ hint) {
   if (d_n) { const long long dn = *d_n; if (dn < n) n = dn; }  // count produced on the device
+  // flags bit 1: frequencies untouched; bit 2: no row output at all — the caller only wants
+  // the keys resolved (inserted, counted) and `hint[i]` = {slot, ctl} of id i, and moves the
+  // rows itself (expand_plan_kernel)
+  const bool no_out = (flags & 4) != 0;
   // A warp takes `kpw` ids (lanes < kpw probe): small kpw = more warps, so the machine is
   // full even for a 64 K-id batch and instruction latency hides behind other warps.
   constexpr int UNR = UQ / CPL > 0 ? UQ / CPL : 1;  // rows in flight per lane
@@ -121,6 +128,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         }
       } else {
         pos = find_slot(t, key, &s);
+        if (pos >= 0) ctl = s.ctl;
         if (pos >= 0 && (s.ctl & CTL_READY) && !(s.ctl & CTL_BLACK)) {
           mode = M_COPY;
           src = row_ptr(t, s.ctl);
@@ -160,7 +168,12 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
     s_src[wib][lane] = src;
     s_mode[wib][lane] = (signed char)mode;
     __syncwarp();
-    for (int it = 0; it < steps; it += UNR) {
+    if (no_out && mode == M_COPY) {
+      // start the row on its way from HBM to L2: the expansion reads it next
+      for (int b = 0; b < dim * 4; b += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src) + b));
+    }
+    for (int it = 0; it < (no_out ? 0 : steps); it += UNR) {
       Chunk<VEC> c[UNR][CPL];
       int m[UNR];
 #pragma unroll
@@ -199,9 +212,9 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
       }
     }
     __syncwarp();
-    const bool my_under = INSERT ? !s_big[wib][lane] : false;
+    const bool my_under = (INSERT && !no_out) ? !s_big[wib][lane] : false;
     __syncwarp();
-    if (INSERT && mode == M_COPY && my_under != ((ctl & CTL_UNDER) != 0)) {
+    if (INSERT && !no_out && mode == M_COPY && my_under != ((ctl & CTL_UNDER) != 0)) {
       if (my_under) atomicOr(&t.slots[pos].ctl, CTL_UNDER);
       else atomicAnd(&t.slots[pos].ctl, ~CTL_UNDER);
     }
@@ -222,21 +235,30 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
         long long r1, r2;
         init_rows_of(t, k, &r1, &r2);
         bool big = false;
-        float* op = out_row<SEG>(out, seg_out, seg_len, base + kl, dim);
+        float* op = no_out ? nullptr : out_row<SEG>(out, seg_out, seg_len, base + kl, dim);
         for (int j = lane; j < nvec; j += 32) {
           Chunk<VEC> c;
           init_chunk<VEC>(t, r1, r2, j * VEC, c);
-          c.store(op + j * VEC);
+          if (!no_out) c.store(op + j * VEC);
           if (m == M_CLAIM) c.store(dr + j * VEC);
           big |= chunk_over_cutoff(c, DEFAULT_CUTOFF);
         }
         const unsigned bal = __ballot_sync(FULL, big);
         __syncwarp();
         if (m == M_CLAIM && lane == kl) {
+          ctl = CTL_READY | (bal ? 0u : CTL_UNDER) | ctl;
           __threadfence();
-          st_release_u32(&t.slots[pos].ctl, CTL_READY | (bal ? 0u : CTL_UNDER) | ctl);
+          st_release_u32(&t.slots[pos].ctl, ctl);
         }
       }
+    }
+    if (hint != nullptr && valid) {
+      // M_FRESH (a duplicate of a key another lane is inserting) cannot happen for the
+      // deduplicated ids a plan hands in; it reports "no slot" and the consumer probes
+      uint2 h;
+      h.x = (pos >= 0 && mode != M_FRESH) ? (uint32_t)pos : 0xffffffffu;
+      h.y = (pos >= 0 && mode != M_FRESH) ? ctl : 0u;
+      hint[i] = h;
     }
   }
 #ifdef KVHBM_TRACE
@@ -257,53 +279,6 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
 // in shared memory in id order and leave with ONE bulk store (shared -> global) of up to
 // 32 x row bytes.  SASS: UBLKCP.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-  return static_cast<unsigned>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes,
-                                          unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-               "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
 template <bool INSERT>
 __global__ void __launch_bounds__(128)
 gather_bulk_kernel(TableView t, const long long* __restrict__ ids,
@@ -751,9 +726,10 @@ __global__ void scatter_rows_n_kernel(const float* __restrict__ src, const int* 
 template <int VEC, int CPL>
 int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts, int64_t n,
                   float* out, uint16_t today, cudaStream_t st, int tpr,
-                  float* const* seg_out = nullptr, int seg_len = 0, const int32_t* d_n = nullptr) {
+                  float* const* seg_out = nullptr, int seg_len = 0, const int32_t* d_n = nullptr,
+                  uint2* hint = nullptr) {
   static const int use_bulk = getenv("KVHBM_GATHER_BULK") ? atoi(getenv("KVHBM_GATHER_BULK")) : 0;
-  if (use_bulk && !seg_out && !d_n && VEC == 4 && tb->dim * 4 <= 1024) {
+  if (use_bulk && !seg_out && !d_n && !hint && out && VEC == 4 && tb->dim * 4 <= 1024) {
     // 4 warps x 32 rows of staging per block
     const int kpi = 32 / tpr;
     int kpw = 32;
@@ -777,9 +753,8 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
     KV_LAUNCHED();
     return 0;
   }
-  static const int uq = getenv("KVHBM_GATHER_UQ") ? atoi(getenv("KVHBM_GATHER_UQ")) : 8;
   static const int bs = getenv("KVHBM_GATHER_BS") ? atoi(getenv("KVHBM_GATHER_BS")) : 128;
-  static const int flags = getenv("KVHBM_GATHER_FLAGS") ? atoi(getenv("KVHBM_GATHER_FLAGS")) : 0;
+  const int flags = out == nullptr && seg_out == nullptr ? 4 : 0;
   static const int kpw_env = getenv("KVHBM_GATHER_KPW") ? atoi(getenv("KVHBM_GATHER_KPW")) : 0;
   // ids per warp: measured on B200, a 64 K-id batch is fastest with 32 ids per warp (one
   // wave of ~14 warps per SM, 8 rows in flight per lane); smaller batches use fewer ids per
@@ -789,15 +764,21 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
   const long long max_warps = (long long)sm_count(tb->device) * 8;
   while (kpw < 32 && (n + kpw - 1) / kpw > max_warps) kpw <<= 1;
   if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
+  if (flags & 4) {  // probe only: nothing to move, so a lane per id as soon as the chip is full
+    static const int kpw_p = getenv("KVHBM_PROBE_KPW") ? atoi(getenv("KVHBM_PROBE_KPW")) : 0;
+    kpw = kpi;
+    while (kpw < 32 && (n + kpw - 1) / kpw > (long long)sm_count(tb->device) * 16) kpw <<= 1;
+    if (kpw_p >= kpi && kpw_p <= 32) kpw = kpw_p;
+  }
   const long long warps = (n + kpw - 1) / kpw;
   const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const long long* k = reinterpret_cast<const long long*>(ids);
-#define KV_G(INS, Q) gather_kernel<VEC, CPL, INS, Q, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0, d_n)
+#define KV_G(INS) gather_kernel<VEC, CPL, INS, 8, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0, d_n, hint)
   if (seg_out) {
     gather_kernel<VEC, CPL, true, 8, true><<<blocks, bs, 0, st>>>(
-        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len, d_n);
-  } else if (insert) { if (uq == 4) KV_G(true, 4); else if (uq == 8) KV_G(true, 8); else KV_G(true, 16); }
-  else { if (uq == 4) KV_G(false, 4); else if (uq == 8) KV_G(false, 8); else KV_G(false, 16); }
+        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len, d_n, hint);
+  } else if (insert) KV_G(true);
+  else KV_G(false);
 #undef KV_G
   KV_LAUNCHED();
   return 0;
@@ -833,6 +814,116 @@ int launch_insert(Table* tb, const int64_t* ids, const float* values, int64_t n,
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Second half of the planned lookup: out[i, :] = row of uniq[idx[i]], for every position of the
+// batch.  The keys were resolved (inserted, counted) once per DISTINCT id by gather_kernel in
+// its no-output mode, which left {slot, ctl} per distinct id in plan.hint; here nothing probes:
+// a warp takes `kpw` positions, one lane per position reads idx and the hint (L2), then tiles
+// move the rows, UQ in flight per lane.  The tile that handles an id's FIRST occurrence also
+// performs FindOrInsert's UpdateUnderThreshold for it (kv_variable.h:329).
+// ---------------------------------------------------------------------------
+template <int VEC, int CPL, bool INSERT>
+__global__ void __launch_bounds__(256)
+expand_plan_kernel(TableView t, const int* __restrict__ idx, const uint2* __restrict__ hint,
+                   const int* __restrict__ first, long long n, float* __restrict__ out, int tpr,
+                   int kpw) {
+  constexpr int UNR = 8 / CPL > 0 ? 8 / CPL : 1;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long wpb = blockDim.x >> 5;
+  const long long warp0 = blockIdx.x * wpb + wib;
+  const long long nwarps = gridDim.x * wpb;
+  const int kpi = 32 / tpr;
+  const int tl = lane & (tpr - 1);
+  const int tq = lane / tpr;
+  const unsigned tmask = tpr == 32 ? FULL : ((1u << tpr) - 1u);
+  const int dim = t.dim;
+  const int steps = kpw / kpi;
+  __shared__ const float* s_src[8][32];
+  __shared__ unsigned char s_big[8][32];
+  for (long long base = warp0 * kpw; base < n; base += nwarps * kpw) {
+    const long long i = base + lane;
+    const bool valid = lane < kpw && i < n;
+    const float* src = nullptr;
+    uint2 h = make_uint2(0xffffffffu, 0u);
+    bool lead = false;
+    if (valid) {
+      const int r = idx[i];
+      h = __ldg(hint + r);
+      if (INSERT) lead = __ldg(first + r) == (int)i;
+      if (h.x != 0xffffffffu && (h.y & CTL_READY) && !(h.y & CTL_BLACK)) src = row_ptr(t, h.y);
+    }
+    s_src[wib][lane] = src;
+    __syncwarp();
+    for (int it = 0; it < steps; it += UNR) {
+      Chunk<VEC> c[UNR][CPL];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (it + u < steps) {
+          const float* sp = s_src[wib][(it + u) * kpi + tq];
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            if (sp != nullptr && off < dim) c[u][q].load_cg(sp + off);
+            else chunk_zero(c[u][q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (it + u < steps) {
+          const int kl = (it + u) * kpi + tq;
+          bool big = false;
+          if (base + kl < n) {
+            float* op = out + (base + kl) * (long long)dim;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              const int off = (q * tpr + tl) * VEC;
+              if (off < dim) c[u][q].store_stream(op + off);
+              big |= chunk_over_cutoff(c[u][q], DEFAULT_CUTOFF);
+            }
+          }
+          if (INSERT) {
+            const unsigned bal = __ballot_sync(FULL, big);
+            if (tl == 0) s_big[wib][kl] = ((bal >> (tq * tpr)) & tmask) != 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (INSERT && lead && src != nullptr) {
+      const bool under = !s_big[wib][lane];
+      if (under != ((h.y & CTL_UNDER) != 0)) {
+        if (under) atomicOr(&t.slots[h.x].ctl, CTL_UNDER);
+        else atomicAnd(&t.slots[h.x].ctl, ~CTL_UNDER);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int VEC, int CPL>
+int launch_expand_plan(Table* tb, bool insert, const PlanView& pv, const int* first, float* out,
+                       cudaStream_t st, int tpr) {
+  static const int kpw_env = getenv("KVHBM_EXPAND_KPW") ? atoi(getenv("KVHBM_EXPAND_KPW")) : 0;
+  static const int bs = getenv("KVHBM_EXPAND_BS") ? atoi(getenv("KVHBM_EXPAND_BS")) : 256;
+  const long long n = pv.n;
+  const int kpi = 32 / tpr;
+  int kpw = kpi;
+  const long long max_warps = (long long)sm_count(tb->device) * 16;
+  while (kpw < 32 && (n + kpw - 1) / kpw > max_warps) kpw <<= 1;
+  if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
+  const long long warps = (n + kpw - 1) / kpw;
+  const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
+  const uint2* hint = reinterpret_cast<const uint2*>(pv.hint);
+  if (insert)
+    expand_plan_kernel<VEC, CPL, true><<<blocks, bs, 0, st>>>(tb->view(), pv.idx, hint, first, n, out, tpr, kpw);
+  else
+    expand_plan_kernel<VEC, CPL, false><<<blocks, bs, 0, st>>>(tb->view(), pv.idx, hint, first, n, out, tpr, kpw);
+  KV_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
 // Dispatch on the row geometry.  (VEC, CPL) is one of (4|1) x (1|2|4).
@@ -856,6 +947,24 @@ int do_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* counts,
   if (insert) KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
 #define CALL(V, C) launch_gather<V, C>(tb, insert, ids, counts, n, out, today, st, g.tpr, nullptr, 0, d_n)
+  KV_DISPATCH_GEOM(g, CALL);
+#undef CALL
+}
+
+// The lookup of a whole batch through its dedup plan: every distinct id is resolved once
+// (FindOrInsert with the id's occurrence count, or FindOrZeros), then the rows are expanded to
+// all positions.  Same table state and same output as do_gather over the raw ids.
+int do_gather_plan(Table* tb, bool insert, const PlanView& pv, const int* first, float* out,
+                   uint16_t today, cudaStream_t st) {
+  if (pv.n <= 0) return 0;
+  if (insert) KV_TRY(tb->ensure(pv.n, st));
+  RowGeom g = row_geom(tb->dim);
+  uint2* hint = reinterpret_cast<uint2*>(pv.hint);
+  const int64_t* ids = reinterpret_cast<const int64_t*>(pv.uniq);
+#define CALL(V, C) [&]() { \
+    int rc = launch_gather<V, C>(tb, insert, ids, insert ? pv.counts : nullptr, pv.n, nullptr, today, st, g.tpr, nullptr, 0, pv.num, hint); \
+    if (rc) return rc; \
+    return launch_expand_plan<V, C>(tb, insert, pv, first, out, st, g.tpr); }()
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL
 }

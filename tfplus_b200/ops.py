@@ -568,6 +568,174 @@ def kv_variable_sparse_apply_adam_dev(var, m_v, grad, indices, hparams, num_indi
 
 
 # ---------------------------------------------------------------------------
+# dedup plan: unique_with_counts + occurrence lists of one batch (kvhbm.h kv_plan_*)
+# ---------------------------------------------------------------------------
+OPT_ADAGRAD, OPT_GROUP_ADAM_V4, OPT_SPARSE_GROUP_FTRL, OPT_ADAM = 0, 1, 2, 3
+OPT_GROUP_ADAM_V3, OPT_SPARSE_FTRL_V2, OPT_GROUP_SPARSE_FTRL_V2 = 4, 5, 6
+_N_HP = {0: 1, 1: 9, 2: 6, 3: 6, 4: 9, 5: 6, 6: 6}
+
+
+class Plan:
+  """Device-resident dedup plan of up to `max_ids` ids (buffers allocated once).  build(ids)
+  runs tf.unique_with_counts plus the per-id occurrence lists on the current stream; the
+  arrays are views of the plan's own memory (valid until the next build)."""
+
+  def __init__(self, max_ids, device):
+    import ctypes as C
+    self.device = torch.device(device)
+    if self.device.index is None:
+      self.device = torch.device("cuda", torch.cuda.current_device())
+    self.max_ids = int(max_ids)
+    out = C.c_void_p()
+    with torch.cuda.device(self.device):
+      check(_lib.load().kv_plan_create(self.max_ids, C.byref(out)))
+    self.ptr = out.value
+    self.n = 0
+
+  def __del__(self):
+    try:
+      if self.ptr:
+        _lib.load().kv_plan_destroy(self.ptr)
+        self.ptr = None
+    except Exception:
+      pass
+
+  def build(self, ids, ws=None):
+    if ids.device.type != "cuda":
+      raise RuntimeError("plan: ids must live on a CUDA device")
+    ids = ids.contiguous()
+    if ids.dtype != torch.int64:
+      raise NotImplementedError("Unimplemented: only int64 keys")
+    self.ids = ids   # the kernels of this batch read them later: keep them alive
+    self.n = ids.numel()
+    ws = ws or Workspace.get(self.device)
+    with torch.cuda.device(self.device):
+      check(_lib.load().kv_plan_build(self.ptr, ws.ptr, ids.data_ptr(), self.n,
+                                      _stream(self.device)))
+    return self
+
+  def arrays(self):
+    """(uniq i64[n], idx i32[n], counts i32[n], num_unique i32[1], seg_off i32[n], pos i32[n]):
+    zero-copy views of the plan's device arrays; entries past num_unique are undefined and the
+    contents change with the next build."""
+    import ctypes as C
+    ptrs = [C.c_void_p() for _ in range(6)]
+    check(_lib.load().kv_plan_arrays(self.ptr, *[C.byref(p) for p in ptrs]))
+    n = self.n
+    specs = [("<i8", n, torch.int64), ("<i4", n, torch.int32), ("<i4", n, torch.int32),
+             ("<i4", 1, torch.int32), ("<i4", n, torch.int32), ("<i4", n, torch.int32)]
+    out = []
+    for p, (ts, cnt, dt) in zip(ptrs, specs):
+      if cnt == 0:
+        out.append(torch.empty(0, dtype=dt, device=self.device))
+      else:
+        out.append(torch.as_tensor(_DevArray(p.value, cnt, ts, self), device=self.device))
+    return tuple(out)
+
+
+class _DevArray:
+  """__cuda_array_interface__ view of device memory owned by `owner`."""
+
+  def __init__(self, ptr, n, typestr, owner):
+    self.owner = owner
+    self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                     "version": 2}
+
+
+def kv_variable_gather_or_insert_plan(table_handle, plan, out=None):
+  """KvVariableGatherOrInsertV2 over the batch `plan` was built from: every distinct id is
+  looked up once with its occurrence count, rows are expanded to all positions."""
+  h = table_handle
+  if out is None:
+    out = torch.empty((plan.n, h.dim), dtype=torch.float32, device=h.device)
+  with torch.cuda.device(h.device):
+    check(h._lib.kv_gather_or_insert_plan(h._live(), plan.ptr, out.data_ptr(), today(), h.stream))
+  return out
+
+
+def kv_variable_gather_or_zeros_plan(table_handle, plan, out=None):
+  h = table_handle
+  if out is None:
+    out = torch.empty((plan.n, h.dim), dtype=torch.float32, device=h.device)
+  with torch.cuda.device(h.device):
+    check(h._lib.kv_gather_or_zeros_plan(h._live(), plan.ptr, out.data_ptr(), h.stream))
+  return out
+
+
+def segment_sum_plan(plan, data, out=None):
+  """tf.math.unsorted_segment_sum(data, plan.idx, num_unique): rows [0, num_unique) of `out`
+  ([n, dim]) are written, every segment summed in increasing position (TF's CPU order)."""
+  data = data.contiguous()
+  dim = data.shape[1]
+  if out is None:
+    out = torch.empty((plan.n, dim), dtype=torch.float32, device=data.device)
+  with torch.cuda.device(data.device):
+    check(_lib.load().kv_segment_sum_plan(plan.ptr, data.data_ptr(), dim, out.data_ptr(),
+                                          _stream(data.device)))
+  return out
+
+
+def kv_variable_apply_plan(kind, var, slot_a, slot_b, plan, grad, hparams, update_slots=True,
+                           advance_powers=False):
+  """UnsortedSegmentSum + the KvVariable*Apply* op `kind` (OPT_*) in one launch.  grad[n, dim]
+  has one row per id occurrence of the plan's batch.  hparams: a python sequence of the op's
+  scalar inputs in op order (host path, validated as the reference validates them) or a float32
+  device tensor of them (graph-capturable; advance_powers then also does Adam's _finish)."""
+  import ctypes as C
+  g = grad.contiguous()
+  if g.dtype != torch.float32:
+    raise NotImplementedError("Unimplemented: only float32 gradients")
+  if g.shape[0] != plan.n:
+    raise ValueError("InvalidArgument: grad must be the same size as indices in the first "
+                     "dimension.")
+  if g.numel() != plan.n * var.dim:
+    raise ValueError("InvalidArgument: var and grad must match in dimension 1")
+  lib = var._lib
+  b = slot_b._live() if slot_b is not None else None
+  with torch.cuda.device(var.device):
+    if isinstance(hparams, torch.Tensor):
+      hp = _hp(var, hparams, _N_HP[kind])
+      check(lib.kv_apply_plan_dev(kind, var._live(), slot_a._live(), b, plan.ptr, g.data_ptr(),
+                                  hp.data_ptr(), int(bool(advance_powers)),
+                                  int(bool(update_slots)), today(), var.stream))
+    else:
+      arr = (C.c_float * len(hparams))(*[float(x) for x in hparams])
+      check(lib.kv_apply_plan(kind, var._live(), slot_a._live(), b, plan.ptr, g.data_ptr(), arr,
+                              len(hparams), int(bool(update_slots)), today(), var.stream))
+
+
+def kv_variable_group_sparse_apply_adam_v3(var, m_v_linear, grad, indices, lr, beta1_power,
+                                           beta2_power, beta1, beta2, epsilon, l1, l2, l21,
+                                           use_locking=False, num_indices=None):
+  """ops/training_ops.cc:1086-1105."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  check(var._lib.kv_apply_group_adam_v3(var._live(), m_v_linear._live(), ids.data_ptr(),
+                                        g.data_ptr(), ids.numel(), _ptr(dn), lr, beta1_power,
+                                        beta2_power, beta1, beta2, epsilon, l1, l2, l21, today(),
+                                        var.stream))
+
+
+def kv_variable_sparse_apply_ftrl_v2(var, accum, linear, grad, indices, lr, l1, l2, l2_shrinkage,
+                                     lr_power, use_locking=False, num_indices=None):
+  """ops/training_ops.cc:103-117."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  check(var._lib.kv_apply_sparse_ftrl_v2(var._live(), accum._live(), linear._live(),
+                                         ids.data_ptr(), g.data_ptr(), ids.numel(), _ptr(dn), lr,
+                                         l1, l2, l2_shrinkage, lr_power, today(), var.stream))
+
+
+def kv_variable_group_sparse_apply_ftrl_v2(var, accum, linear, grad, indices, lr, l1, l2,
+                                           l2_shrinkage, lr_power, use_locking=False,
+                                           num_indices=None):
+  """ops/training_ops.cc:119-133."""
+  ids, g, dn = _apply_args(var, grad, indices, num_indices)
+  check(var._lib.kv_apply_group_sparse_ftrl_v2(var._live(), accum._live(), linear._live(),
+                                               ids.data_ptr(), g.data_ptr(), ids.numel(),
+                                               _ptr(dn), lr, l1, l2, l2_shrinkage, lr_power,
+                                               today(), var.stream))
+
+
+# ---------------------------------------------------------------------------
 # stock TF ops on the path
 # ---------------------------------------------------------------------------
 def unique(x, with_counts=False, sync=True):
