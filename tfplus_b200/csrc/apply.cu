@@ -15,8 +15,6 @@
 
 namespace kvhbm {
 
-int set_trace_apply(unsigned long long*) { return 0; }
-
 namespace {
 
 // The fused apply over deduplicated ids with their gradients already summed (the op surface of

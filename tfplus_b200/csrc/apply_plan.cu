@@ -33,84 +33,219 @@ PlanView plan_view(const Plan* p);
 int plan_need_scratch(Plan* p, int dim, cudaStream_t st);
 int apply_validate(int kind, Table* var, Table* sa, Table* sb, const float* hp);
 
+// Optional per-warp timeline of the fused kernel (scripts/trace_apply_plan.py; compiled in by
+// KVHBM_TRACE=1): {start, heavy items done, light groups done, groups taken} in ns.
+__device__ unsigned long long* g_trace_plan = nullptr;
+int set_trace_apply(unsigned long long* d_buf) {
+  KV_CUDA(cudaMemcpyToSymbol(g_trace_plan, &d_buf, sizeof(d_buf)));
+  return 0;
+}
+
 namespace {
 
-constexpr int AP_THREADS = 320;  // warp 0: heavy consumer, warp 1: heavy producer, 2..9: light ids
+#ifdef KVHBM_TRACE
+__device__ __forceinline__ unsigned long long gtime_plan() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
+constexpr int AP_THREADS = 320;
 constexpr int AP_NW = AP_THREADS / 32;
-constexpr int RING_ROWS = 64;    // occurrence rows per ring stage
+constexpr int RING_ROWS = 64;     // occurrence rows per ring stage
 constexpr int RING_STAGES = 10;
-constexpr int RING_PITCH = 128;  // bytes per row part (32 columns)
+constexpr int RING_PITCH = 128;   // bytes per row part (32 columns)
 constexpr int RING_BYTES = RING_STAGES * RING_ROWS * RING_PITCH;  // 80 KB
 
+// The block's ring of stages.  `no` counts the stages the block has been through since the
+// launch started (the same number in the consumer and the producer): stage `no` lives in ring
+// entry no % STAGES and is use number no / STAGES of that entry.
 struct Ring {
   unsigned char* base;
   unsigned long long* full;
   unsigned long long* empty;
-  int stage;
-  unsigned par;
-  __device__ __forceinline__ void advance() {
-    if (++stage == RING_STAGES) { stage = 0; par ^= 1u; }
-  }
+  unsigned no;
+#ifdef KVHBM_TRACE
+  long long waited;   // cycles the consumer spent waiting for full stages
+  long long t_chain;  // cycles of the first chain this warp walked
+#endif
 };
 
-// Consumer side of one heavy work item: the sum of column `col` over the item's `c`
-// occurrence rows in list order, out of the ring (ringed) or straight from memory.
-__device__ __forceinline__ float heavy_consume(Ring& rg, bool ringed, const float* __restrict__ grad,
-                                               const int* __restrict__ list, int c, int dim,
-                                               int col, bool act, int lane) {
-  float acc = 0.f;
-  if (ringed) {
-    for (int k0 = 0; k0 < c; k0 += RING_ROWS) {
-      mbar_wait(&rg.full[rg.stage], rg.par);
-      const float* st = reinterpret_cast<const float*>(rg.base + (size_t)rg.stage * RING_ROWS * RING_PITCH);
-      const int rows = c - k0 < RING_ROWS ? c - k0 : RING_ROWS;
-      if (rows == RING_ROWS) {
-#pragma unroll 16
-        for (int j = 0; j < RING_ROWS; ++j) acc += st[j * 32 + lane];
-      } else {
-        for (int j = 0; j < rows; ++j) acc += st[j * 32 + lane];
+// Why the heavy rows are staged first (measured on B200, scripts/ub/rowgather*.cu): one SM
+// pulls randomly placed 128-byte lines out of HBM at ~22 GB/s with 9 warps x 16 loads in flight
+// (a warp gets ~30 lines per microsecond, whatever the load flavour), while a chain that adds
+// one row every 4 cycles consumes 63 GB/s.  Bulk copies of single rows (cp.async.bulk, 128 B
+// each) and 16-byte cp.async fed the chain at 40 / 9 ns per row instead of the 2 ns it needs.
+// So the random part of the access is spread over the whole chip: stage_heavy_kernel copies
+// the occurrence rows of heavy ids into list order (one contiguous run per id and 32-column
+// part, 8.8 MB at the microbench), and the chain's feed becomes 8 KB contiguous bulk copies
+// out of L2, which a single thread keeps in flight.
+//
+// Staged layout, per 32-column part: "units" of four consecutive entries of pos (4 rows x 32
+// columns, 512 bytes), stored column by column — float 4*c + j of unit u is column c of entry
+// 4*u + j — so that a chain lane reads four consecutive rows of its column with one 128-bit
+// shared-memory load, conflict-free across the warp.  Part p starts at unit p * staged_units.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+stage_heavy_kernel(const __grid_constant__ PlanView pl, const float* __restrict__ grad, int dim) {
+  const long long n = pl.n;
+  const long long units = (n + 3) >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    // a thread owns (unit, part, 4 columns): four 16-byte row loads, a 4x4 transpose in
+    // registers, 64 contiguous bytes out
+    const int cpr = dim >> 2;                          // 16-byte chunks per row
+    const long long total = units * cpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
+      const long long u = t / cpr;
+      const int ch = (int)(t - u * cpr), part = ch >> 3, cc = ch & 7;
+      const unsigned fl = *reinterpret_cast<const unsigned*>(pl.eflag + 4 * u);   // 4 entry flags
+      if (fl == 0u) continue;
+      const int4 pz = *reinterpret_cast<const int4*>(pl.pos + 4 * u);
+      const int pzs[4] = {pz.x, pz.y, pz.z, pz.w};
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((fl >> (8 * j)) & 0xffu)
+          v[j] = __ldcs(reinterpret_cast<const float4*>(grad + (long long)pzs[j] * dim + ch * 4));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty[rg.stage]);
-      rg.advance();
+      float4* o = reinterpret_cast<float4*>(pl.staged + ((((long long)part * pl.staged_units + u) << 5) + cc * 4) * 4);
+      o[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+      o[1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+      o[2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+      o[3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
     }
   } else {
-    for (int k0 = 0; k0 < c; k0 += 8) {
-      float t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        t[j] = (act && k0 + j < c) ? __ldcs(grad + (long long)__ldg(list + k0 + j) * dim + col) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (k0 + j < c) acc += t[j];
+    const long long total = n * dim;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += stride) {
+      const long long e = t / dim;
+      const int col = (int)(t - e * dim);
+      if (!pl.eflag[e]) continue;
+      const float v = __ldcs(grad + (long long)__ldg(pl.pos + e) * dim + col);
+      pl.staged[(((((long long)(col >> 5) * pl.staged_units + (e >> 2)) << 5) + (col & 31)) << 2) + (e & 3)] = v;
+    }
+  }
+}
+
+// One heavy work item = the sum of a 32-column part of one id's occurrence rows — entries
+// [e0, e0 + c) of pos — in list order from +0.  Warp 0 walks the chain out of the ring, one
+// column per lane, four units (16 rows) pulled into registers ahead of the adds so that the
+// chain itself is nothing but dependent FADDs; lane 0 of warp 1 keeps the ring full with one
+// bulk copy per stage (16 units, 8 KB) out of the staged part `part0` (unit 0 of the part).
+// The first and the last stage may hold rows of neighbouring ids: they are added under a
+// predicate, the stages in between unconditionally.  Returns the sum (warp 0).
+__device__ __forceinline__ float chain_item(Ring& rg, int wib, int lane, const float* __restrict__ part0,
+                                            int e0, int c, int dbg = 0) {
+  constexpr int SU = RING_ROWS / 4;     // units per stage
+  const int e1 = e0 + c;
+  const int u0 = e0 >> 2, u1 = (e1 + 3) >> 2;
+  const int nst = (u1 - u0 + SU - 1) / SU;
+  const unsigned no0 = rg.no;
+  rg.no += (unsigned)nst;
+  float acc = 0.f;
+  if (wib == 0) {
+#ifdef KVHBM_TRACE
+    const long long tc0 = clock64();
+#endif
+    float4 a[4], b[4];
+    const float4* st = nullptr;
+#define KV_LOAD(dst, c0) _Pragma("unroll") for (int j = 0; j < 4; ++j) dst[j] = st[((c0) * 4 + j) * 32]
+#define KV_ADD(v) if (dbg != 2) { _Pragma("unroll") for (int j = 0; j < 4; ++j) { acc += v[j].x; acc += v[j].y; acc += v[j].z; acc += v[j].w; } } else { acc += v[0].x + v[1].x + v[2].x + v[3].x; }
+    bool have_a = false;
+    for (int s = 0; s < nst; ++s) {
+      const unsigned no = no0 + (unsigned)s;
+      const unsigned e = no % RING_STAGES;
+      if (!have_a) {
+#ifdef KVHBM_TRACE
+        const long long w0 = clock64();
+#endif
+        mbar_wait(&rg.full[e], (no / RING_STAGES) & 1u);
+#ifdef KVHBM_TRACE
+        rg.waited += clock64() - w0;
+#endif
+        st = reinterpret_cast<const float4*>(rg.base + (size_t)e * RING_ROWS * RING_PITCH) + lane;
+      }
+      if (s == 0 || s == nst - 1) {
+        const int ub = u0 + s * SU;
+        const int nun = u1 - ub < SU ? u1 - ub : SU;
+        for (int j = 0; j < nun; ++j) {
+          const float4 v = st[j * 32];
+          const int row = (ub + j) * 4;
+          if (row >= e0 && row < e1) acc += v.x;
+          if (row + 1 >= e0 && row + 1 < e1) acc += v.y;
+          if (row + 2 >= e0 && row + 2 < e1) acc += v.z;
+          if (row + 3 >= e0 && row + 3 < e1) acc += v.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty[e]);
+        have_a = false;
+      } else {
+        if (!have_a) KV_LOAD(a, 0);
+        KV_LOAD(b, 1);
+        KV_ADD(a);
+        KV_LOAD(a, 2);
+        KV_ADD(b);
+        KV_LOAD(b, 3);
+        KV_ADD(a);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty[e]);   // the stage is in registers: hand it back
+        if (s + 1 < nst - 1) {                      // the next stage is an interior one too
+          const unsigned e1n = (no + 1u) % RING_STAGES, par = ((no + 1u) / RING_STAGES) & 1u;
+#ifdef KVHBM_TRACE
+          const long long w0 = clock64();
+#endif
+          unsigned ok = mbar_test(&rg.full[e1n], par);
+          KV_ADD(b);
+          while (!ok) ok = mbar_test(&rg.full[e1n], par);
+#ifdef KVHBM_TRACE
+          rg.waited += clock64() - w0;
+#endif
+          st = reinterpret_cast<const float4*>(rg.base + (size_t)e1n * RING_ROWS * RING_PITCH) + lane;
+          KV_LOAD(a, 0);
+          have_a = true;
+        } else {
+          KV_ADD(b);
+          have_a = false;
+        }
+      }
+    }
+#undef KV_LOAD
+#undef KV_ADD
+#ifdef KVHBM_TRACE
+    if (no0 == 0) rg.t_chain = clock64() - tc0;
+#endif
+  } else if (wib == 1 && lane == 0) {
+    for (int s = 0; s < nst; ++s) {
+      const unsigned no = no0 + (unsigned)s;
+      const unsigned e = no % RING_STAGES, use = no / RING_STAGES;
+      if (use > 0) mbar_wait(&rg.empty[e], (use - 1u) & 1u);
+      const int ub = u0 + s * SU;
+      const int nun = u1 - ub < SU ? u1 - ub : SU;
+      const unsigned bytes = (unsigned)nun * 512u;
+      mbar_arrive_expect_tx(&rg.full[e], bytes);
+      bulk_load(rg.base + (size_t)e * RING_ROWS * RING_PITCH, part0 + (size_t)ub * 128, bytes, &rg.full[e]);
     }
   }
   return acc;
 }
 
-// Producer side: one bulk copy per occurrence row part into the ring, a stage at a time.
-__device__ __forceinline__ void heavy_produce(Ring& rg, const float* __restrict__ g0,
-                                              const int* __restrict__ list, int c, int dim,
-                                              unsigned pb, int lane) {
-  for (int k0 = 0; k0 < c; k0 += RING_ROWS) {
-    mbar_wait(&rg.empty[rg.stage], rg.par ^ 1u);
-    unsigned char* st = rg.base + (size_t)rg.stage * RING_ROWS * RING_PITCH;
-    int pz[RING_ROWS / 32];
-    unsigned bytes = 0;
-#pragma unroll
-    for (int q = 0; q < RING_ROWS / 32; ++q) {
-      const int k = k0 + q * 32 + lane;
-      pz[q] = k < c ? __ldg(list + k) : -1;
-      if (pz[q] >= 0) bytes += pb;
+// Light groups are handed out through a counter in the plan (blocks that spend their time on
+// long chains take fewer); the last block to finish leaves both words at zero.
+__device__ __forceinline__ long long next_light_group(unsigned* work, int kpw, int lane) {
+  unsigned b = 0;
+  if (lane == 0) b = atomicAdd(&work[0], (unsigned)kpw);
+  return (long long)__shfl_sync(0xffffffffu, b, 0);
+}
+__device__ __forceinline__ void work_epilogue(unsigned* work) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&work[1], 1u) == gridDim.x - 1) {
+      work[0] = 0u;
+      work[1] = 0u;
     }
-    if (bytes) mbar_arrive_expect_tx(&rg.full[rg.stage], bytes);
-    else mbar_arrive(&rg.full[rg.stage]);
-#pragma unroll
-    for (int q = 0; q < RING_ROWS / 32; ++q)
-      if (pz[q] >= 0)
-        bulk_load(st + (size_t)(q * 32 + lane) * RING_PITCH, g0 + (long long)pz[q] * dim, pb,
-                  &rg.full[rg.stage]);
-    rg.advance();
   }
 }
 
@@ -135,7 +270,7 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
                   const __grid_constant__ TableView sb, const __grid_constant__ PlanView pl,
                   const float* __restrict__ grad, const __grid_constant__ ApplyParams p_in,
                   const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv,
-                  int use_ring) {
+                  int excl) {
   ApplyParams p = p_in;
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p_in.update_slots);
   __shared__ ApplySmem<AP_NW, VEC, CPL> sm;
@@ -145,10 +280,9 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
   const int dim = var.dim;
   const long long U = *pl.num;
   const long long* ids = pl.uniq;
-  const bool ringed = use_ring && VEC == 4;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     fence_async_smem();
   }
   __syncthreads();
@@ -158,18 +292,25 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
   const int parts = (dim + 31) / 32;
   const long long items = (long long)H * parts;
 
+#ifdef KVHBM_TRACE
+  unsigned long long* trace = g_trace_plan;
+  unsigned long long t_start = 0, t_heavy = 0, n_groups = 0;
+  if (trace) t_start = gtime_plan();
+#endif
+  // ---- heavy ids first: their chains are the longest thing in the launch ----
   Ring rg;
-  rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.stage = 0; rg.par = 0;
-  if (wib == 0) {
-    // ---- heavy consumer: the serial chain of one (id, 32-column part) at a time ----
-    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-      const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-      const int r = pl.heavy[h];
-      const int c = pl.counts[r], off = pl.seg_off[r];
-      const int col = part * 32 + lane;
-      const bool act = col < dim;
-      const float acc = heavy_consume(rg, ringed, grad, pl.pos + off, c, dim, col, act, lane);
-      if (act) __stcg(pl.heavy_sum + (size_t)h * pl.sum_dim + col, acc);
+  rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.no = 0;
+#ifdef KVHBM_TRACE
+  rg.waited = 0; rg.t_chain = 0;
+#endif
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
+    const int r = pl.heavy[h];
+    const int c = pl.counts[r], off = pl.seg_off[r];
+    const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
+    const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128, off, c, excl);
+    if (wib == 0) {
+      if (lane < width) __stcg(pl.heavy_sum + (size_t)h * pl.sum_dim + part * 32 + lane, acc);
       __threadfence();
       unsigned last = 0;
       if (lane == 0) last = atomicAdd(&pl.heavy_done[h], 1u) == (unsigned)(parts - 1);
@@ -182,32 +323,38 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
         apply_heavy_id<VEC, CPL, KIND>(&sm, wib, &var, &sa, &sb, &pl, h, r, &p, today, tpr);
       }
     }
-  } else if (wib == 1) {
-    // ---- heavy producer: keeps the ring full ----
-    if (ringed) {
-      for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-        const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-        const int r = pl.heavy[h];
-        const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
-        heavy_produce(rg, grad + part * 32, pl.pos + pl.seg_off[r], pl.counts[r], dim,
-                      (unsigned)width * 4u, lane);
-      }
-    }
-  } else {
-    // ---- light ids ----
-    const long long lw = (long long)blockIdx.x * (AP_NW - 2) + (wib - 2);
-    const long long nlw = (long long)gridDim.x * (AP_NW - 2);
+  }
+
+  if (excl && blockIdx.x < items) __syncthreads();   // (experiment) light work waits for the chain
+#ifdef KVHBM_TRACE
+  if (trace) t_heavy = gtime_plan();
+#endif
+  // ---- light ids ----
+  {
     GradSrc gs;
     gs.grad = grad; gs.row0 = 0; gs.counts = pl.counts; gs.seg_off = pl.seg_off; gs.pos = pl.pos;
     gs.heavy_t = pl.heavy_t; gs.hint = pl.hint; gs.cg = false;
-    for (long long base = lw * kpw; base < U; base += nlw * kpw)
+    for (;;) {
+      const long long base = next_light_group(pl.work, kpw, lane);
+      if (base >= U) break;
       apply_group<AP_NW, VEC, CPL, KIND, 1, 4>(sm, wib, var, sa, sb, ids, gs, base, U, p, today, tpr,
                                                kpw, false);
+#ifdef KVHBM_TRACE
+      ++n_groups;
+#endif
+    }
   }
+#ifdef KVHBM_TRACE
+  if (trace && lane == 0) {
+    unsigned long long* r = trace + ((size_t)blockIdx.x * AP_NW + wib) * 4;
+    r[0] = t_start; r[1] = t_heavy; r[2] = gtime_plan();
+    r[3] = wib == 0 ? ((unsigned long long)rg.waited & 0xffffffffull) | ((unsigned long long)rg.t_chain << 32) : n_groups;
+  }
+#endif
+  work_epilogue(pl.work);
 
   // AdamOptimizer._finish folded into this launch (see apply.cu)
   if ((KindTraits<KIND>::ADAMISH || KIND == K_ADAM) && d_adv != nullptr) {
-    __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned done = atomicAdd(&var.ctr->apply_done, 1u);
@@ -224,18 +371,18 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
 
 // tf.math.unsorted_segment_sum through the plan, on its own: out[r, :] = sum of the rows
 // data[pos[seg_off[r] + k], :], k = 0 .. counts[r]-1, in that order from +0.  Same roles as the
-// fused kernel: warps 0/1 run the heavy ids' chains through the ring, the others take light
-// segments, a tile per segment.
+// fused kernel: blocks walk the heavy ids' chains through the ring first, then every warp
+// takes light segments, a tile per segment.
+template <int VEC>
 __global__ void __launch_bounds__(AP_THREADS, 2)
 segsum_plan_kernel(const __grid_constant__ PlanView pl, const float* __restrict__ data, int dim,
-                   float* __restrict__ out, int tpr, int vec, int use_ring) {
+                   float* __restrict__ out, int tpr) {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ unsigned long long full_bar[RING_STAGES], empty_bar[RING_STAGES];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long U = *pl.num;
-  const bool ringed = use_ring && vec == 4;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     fence_async_smem();
   }
   __syncthreads();
@@ -244,68 +391,95 @@ segsum_plan_kernel(const __grid_constant__ PlanView pl, const float* __restrict_
   const int parts = (dim + 31) / 32;
   const long long items = (long long)H * parts;
   Ring rg;
-  rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.stage = 0; rg.par = 0;
-  if (wib == 0) {
-    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-      const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-      const int r = pl.heavy[h];
-      const int col = part * 32 + lane;
-      const bool act = col < dim;
-      const float acc = heavy_consume(rg, ringed, data, pl.pos + pl.seg_off[r], pl.counts[r], dim,
-                                      col, act, lane);
-      if (act) out[(long long)r * dim + col] = acc;
-    }
-  } else if (wib == 1) {
-    if (ringed) {
-      for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-        const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-        const int r = pl.heavy[h];
-        const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
-        heavy_produce(rg, data + part * 32, pl.pos + pl.seg_off[r], pl.counts[r], dim,
-                      (unsigned)width * 4u, lane);
-      }
-    }
-  } else {
-    // a tile of `tpr` lanes per segment, elements strided by the tile (any dim)
-    const int tl = lane & (tpr - 1);
-    const long long tile = ((long long)blockIdx.x * (AP_NW - 2) + (wib - 2)) * (32 / tpr) + lane / tpr;
-    const long long ntiles = (long long)gridDim.x * (AP_NW - 2) * (32 / tpr);
-    const int per = (dim / vec + tpr - 1) / tpr;  // chunks per lane (<= 8)
-    for (long long r = tile; r < U; r += ntiles) {
-      const int c = pl.counts[r];
-      if (c > pl.heavy_t) continue;
-      const int* list = pl.pos + pl.seg_off[r];
-      float acc[8][4];
+  rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.no = 0;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
+    const int r = pl.heavy[h];
+    const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
+    const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128,
+                                 pl.seg_off[r], pl.counts[r]);
+    if (wib == 0 && lane < width) out[(long long)r * dim + part * 32 + lane] = acc;
+  }
+  // a tile of `tpr` lanes per light segment, elements strided by the tile (any dim), the rows
+  // of a segment fetched four at a time
+  const int tl = lane & (tpr - 1);
+  const int kpi = 32 / tpr;
+  const int per = (dim / VEC + tpr - 1) / tpr;  // chunks per lane (<= 8)
+  for (;;) {
+    const long long r = next_light_group(pl.work, kpi, lane) + lane / tpr;
+    if (r - lane / tpr >= U) break;
+    const int c = r < U ? pl.counts[r] : 0;
+    if (c == 0 || c > pl.heavy_t) continue;
+    const int* list = pl.pos + pl.seg_off[r];
+    float acc[8][VEC];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 8; ++q)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-      for (int k = 0; k < c; ++k) {
-        const float* row = data + (long long)__ldg(list + k) * dim;
+      for (int e = 0; e < VEC; ++e) acc[q][e] = 0.f;
+    if (per <= 2) {
+      for (int k0 = 0; k0 < c; k0 += 4) {
+        Chunk<VEC> t[4][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int off = (q * tpr + tl) * vec;
-          if (q < per && off < dim) {
-            if (vec == 4) {
-              const float4 v = __ldcs(reinterpret_cast<const float4*>(row + off));
-              acc[q][0] += v.x; acc[q][1] += v.y; acc[q][2] += v.z; acc[q][3] += v.w;
-            } else {
-              acc[q][0] += __ldcs(row + off);
+        for (int j = 0; j < 4; ++j) {
+          if (k0 + j < c) {
+            const float* row = data + (long long)__ldg(list + k0 + j) * dim;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int off = (q * tpr + tl) * VEC;
+              if (q < per && off < dim) t[j][q].load_stream(row + off); else chunk_zero(t[j][q]);
             }
           }
         }
-      }
-      float* o = out + r * dim;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int off = (q * tpr + tl) * vec;
-        if (q < per && off < dim) {
-          if (vec == 4) *reinterpret_cast<float4*>(o + off) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
-          else o[off] = acc[q][0];
+        for (int j = 0; j < 4; ++j)
+          if (k0 + j < c)
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) acc[q][e] += t[j][q].v[e];
+      }
+    } else {
+      for (int k = 0; k < c; ++k) {
+        const float* row = data + (long long)__ldg(list + k) * dim;
+        Chunk<VEC> t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (q < per && off < dim) t[q].load_stream(row + off); else chunk_zero(t[q]);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[q][e] += t[q].v[e];
+      }
+    }
+    float* o = out + r * dim;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int off = (q * tpr + tl) * VEC;
+      if (q < per && off < dim) {
+        Chunk<VEC> w;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) w.v[e] = acc[q][e];
+        w.store(o + off);
       }
     }
   }
+  work_epilogue(pl.work);
+}
+
+// The staging pass that precedes either chain kernel.
+int launch_stage_heavy(const PlanView& pv, const float* data, int dim, int device, cudaStream_t st) {
+  const int vec = (dim & 3) == 0 ? 4 : 1;
+  const long long total = vec == 4 ? ((pv.n + 3) / 4) * (dim / 4) : pv.n * dim;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count(device) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (vec == 4) stage_heavy_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(pv, data, dim);
+  else stage_heavy_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(pv, data, dim);
+  KV_LAUNCHED();
+  return 0;
 }
 
 __global__ void advance_powers_plan_kernel(float* hp, int p, int b) {
@@ -318,17 +492,17 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
                       const ApplyParams& p, const float* d_hp, uint16_t today, cudaStream_t st,
                       int tpr, float* d_adv) {
   static const int kpw_env = getenv("KVHBM_APPLYP_KPW") ? atoi(getenv("KVHBM_APPLYP_KPW")) : 0;
-  static const int ring_env = getenv("KVHBM_APPLYP_RING") ? atoi(getenv("KVHBM_APPLYP_RING")) : 1;
+  static const int excl_env = getenv("KVHBM_APPLYP_EXCL") ? atoi(getenv("KVHBM_APPLYP_EXCL")) : 0;
   static const int bps_env = getenv("KVHBM_APPLYP_BPS") ? atoi(getenv("KVHBM_APPLYP_BPS")) : 2;
   const int sms = sm_count(var->device);
   const int kpi = 32 / tpr;
   // light warps of a full grid; a Zipf batch has ~n/3 distinct ids
-  const long long lwarps = (long long)sms * bps_env * (AP_NW - 2);
+  const long long lwarps = (long long)sms * bps_env * AP_NW;
   const long long n_est = (pv.n + 2) / 3;
   int kpw = kpi;
   while (kpw < 32 && (n_est + kpw - 1) / kpw > lwarps) kpw <<= 1;
   if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
-  long long blocks = ((pv.n + kpw - 1) / kpw + (AP_NW - 3)) / (AP_NW - 2);
+  long long blocks = ((pv.n + kpw - 1) / kpw + AP_NW - 1) / AP_NW;
   if (blocks > (long long)sms * bps_env) blocks = (long long)sms * bps_env;
   if (blocks < 1) blocks = 1;
   auto kern = apply_plan_kernel<VEC, CPL, KIND>;
@@ -338,8 +512,9 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
     attr = true;
   }
   TableView vb = sb ? sb->view() : sa->view();
+  KV_TRY(launch_stage_heavy(pv, grad, var->dim, var->device, st));
   kern<<<(unsigned)blocks, AP_THREADS, RING_BYTES, st>>>(var->view(), sa->view(), vb, pv, grad, p, d_hp,
-                                                        today, tpr, kpw, d_adv, ring_env);
+                                                        today, tpr, kpw, d_adv, excl_env);
   KV_LAUNCHED();
   return 0;
 }
@@ -380,26 +555,31 @@ int dispatch_apply_plan(Table* var, Table* sa, Table* sb, Plan* plan, const floa
 }  // namespace
 
 int do_segment_sum_plan(Plan* plan, const float* data, int dim, float* out, cudaStream_t st) {
+  if (plan_view(plan).n <= 0) return 0;
+  KV_TRY(plan_need_scratch(plan, dim, st));
   const PlanView pv = plan_view(plan);
-  if (pv.n <= 0) return 0;
   RowGeom g = row_geom(dim);
   if (g.cpl > 8) return fail(3, "segment_sum_plan: dim too large");
-  static const int ring_env = getenv("KVHBM_APPLYP_RING") ? atoi(getenv("KVHBM_APPLYP_RING")) : 1;
   static bool attr = false;
   if (!attr) {
-    KV_CUDA(cudaFuncSetAttribute(segsum_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KV_CUDA(cudaFuncSetAttribute(segsum_plan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 RING_BYTES));
+    KV_CUDA(cudaFuncSetAttribute(segsum_plan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  RING_BYTES));
     attr = true;
   }
   int dev = 0;
   KV_CUDA(cudaGetDevice(&dev));
   const int sms = sm_count(dev);
-  const long long tiles_per_block = (long long)(AP_NW - 2) * (32 / g.tpr);
+  const long long tiles_per_block = (long long)AP_NW * (32 / g.tpr);
   long long blocks = (pv.n + tiles_per_block - 1) / tiles_per_block;
   if (blocks > 2LL * sms) blocks = 2LL * sms;
   if (blocks < 1) blocks = 1;
-  segsum_plan_kernel<<<(unsigned)blocks, AP_THREADS, RING_BYTES, st>>>(pv, data, dim, out, g.tpr, g.vec,
-                                                                      ring_env);
+  KV_TRY(launch_stage_heavy(pv, data, dim, dev, st));
+  if (g.vec == 4)
+    segsum_plan_kernel<4><<<(unsigned)blocks, AP_THREADS, RING_BYTES, st>>>(pv, data, dim, out, g.tpr);
+  else
+    segsum_plan_kernel<1><<<(unsigned)blocks, AP_THREADS, RING_BYTES, st>>>(pv, data, dim, out, g.tpr);
   KV_LAUNCHED();
   return 0;
 }

@@ -49,6 +49,16 @@ __device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, unsi
 __device__ __forceinline__ void bulk_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// Ampere-style 16-byte asynchronous copy (SASS LDGSTS) and its completion hooked to an
+// mbarrier: the arrive fires once every cp.async this thread issued before it has landed.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(512)
 plan_sort_heavy_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
                        const int* __restrict__ heavy, const int* __restrict__ heavy_n,
                        int heavy_cap, const int* __restrict__ pos_u, int* __restrict__ pos,
-                       long long n) {
+                       unsigned char* __restrict__ eflag, long long n) {
   __shared__ unsigned bm[PLAN_WORDS];
   __shared__ int wsum[16];
   __shared__ int run_base;
@@ -434,6 +434,7 @@ plan_sort_heavy_kernel(const int* __restrict__ counts, const int* __restrict__ s
         while (bits) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
+          eflag[off + before] = 1;
           pos[off + before++] = (int)(c0 + (long long)w * 32 + b);
         }
       }
@@ -979,13 +980,17 @@ struct Plan {
   int* first = nullptr;
   uint2* hint = nullptr;
   // scratch of the fused apply's heavy path: gradient sums [heavy_cap][sum_dim], arrival counters
+  unsigned char* eflag = nullptr;
   float* heavy_sum = nullptr;
+  float* staged = nullptr;
   int sum_dim = 0;
   unsigned* heavy_done = nullptr;
+  unsigned* work = nullptr;
   void* block = nullptr;
   ~Plan() {
     if (block) cudaFree(block);
     if (heavy_sum) cudaFree(heavy_sum);
+    if (staged) cudaFree(staged);
   }
 };
 
@@ -1013,7 +1018,8 @@ Plan* plan_new(int64_t max_ids, int heavy_t, int* rc) {
   const size_t a_i = align_up((size_t)max_ids * sizeof(int));
   const size_t a_l = align_up((size_t)max_ids * sizeof(long long));
   const size_t a_h = align_up((size_t)p->heavy_cap * sizeof(int));
-  const size_t total = 2 * a_l + 7 * a_i + 2 * a_h + 512;
+  const size_t a_f = align_up((size_t)max_ids);
+  const size_t total = 2 * a_l + 7 * a_i + 2 * a_h + a_f + 512;
   cudaError_t e = cudaMalloc(&p->block, total);
   if (e != cudaSuccess) { *rc = cuda_fail(e, "cudaMalloc(plan)"); delete p; return nullptr; }
   cudaMemset(p->block, 0, total);
@@ -1029,8 +1035,10 @@ Plan* plan_new(int64_t max_ids, int heavy_t, int* rc) {
   p->hint = reinterpret_cast<uint2*>(c); c += a_l;
   p->heavy = reinterpret_cast<int*>(c); c += a_h;
   p->heavy_done = reinterpret_cast<unsigned*>(c); c += a_h;
+  p->eflag = reinterpret_cast<unsigned char*>(c); c += a_f;
   p->num = reinterpret_cast<int*>(c); c += 256;
   p->heavy_n = reinterpret_cast<int*>(c);
+  p->work = reinterpret_cast<unsigned*>(c + 128);
   plan_forget_hints(p, 0);
   return p;
 }
@@ -1041,6 +1049,8 @@ PlanView plan_view(const Plan* p) {
   v.uniq = p->uniq; v.idx = p->idx; v.counts = p->counts; v.num = p->num;
   v.seg_off = p->seg_off; v.pos = p->pos; v.heavy = p->heavy; v.heavy_n = p->heavy_n;
   v.first = p->first; v.hint = p->hint; v.heavy_sum = p->heavy_sum; v.heavy_done = p->heavy_done;
+  v.work = p->work; v.eflag = p->eflag; v.staged = p->staged;
+  v.staged_units = (p->cap + 3) / 4 + 1;
   v.heavy_t = p->heavy_t; v.heavy_cap = p->heavy_cap; v.sum_dim = p->sum_dim; v.n = p->n;
   return v;
 }
@@ -1056,8 +1066,10 @@ int plan_need_scratch(Plan* p, int dim, cudaStream_t st) {
     return fail(2, "plan: scratch must be sized before CUDA-graph capture (run once eagerly)");
   KV_CUDA(cudaStreamSynchronize(st));
   if (p->heavy_sum) cudaFree(p->heavy_sum);
-  p->heavy_sum = nullptr;
+  if (p->staged) cudaFree(p->staged);
+  p->heavy_sum = p->staged = nullptr;
   KV_CUDA(cudaMalloc(&p->heavy_sum, (size_t)p->heavy_cap * want * sizeof(float)));
+  KV_CUDA(cudaMalloc(&p->staged, (size_t)((p->cap + 3) / 4 + 1) * 4 * want * sizeof(float)));
   p->sum_dim = want;
   return 0;
 }
@@ -1076,13 +1088,14 @@ int do_plan_build(Plan* p, Workspace* ws, const int64_t* ids, int64_t n, cudaStr
   KV_TRY(do_unique_impl(ws, ids, n, reinterpret_cast<int64_t*>(p->uniq), p->idx, p->counts, p->num,
                         nullptr, st, &po));
   const int dev = p->device;
+  KV_CUDA(cudaMemsetAsync(p->eflag, 0, (size_t)((n + 3) & ~3LL), st));  // read four at a time
   // one warp per 32 distinct ids; U <= n
   plan_sort_light_kernel<<<blocks_for((n + 31) / 32 * 32, 256, dev, 8), 256, 0, st>>>(
       p->counts, p->seg_off, p->num, p->pos_u, p->pos, p->heavy_t);
   KV_LAUNCHED();
   int hb = p->heavy_cap < 2 * sm_count(dev) ? p->heavy_cap : 2 * sm_count(dev);
   plan_sort_heavy_kernel<<<hb, 512, 0, st>>>(p->counts, p->seg_off, p->heavy, p->heavy_n,
-                                             p->heavy_cap, p->pos_u, p->pos, n);
+                                             p->heavy_cap, p->pos_u, p->pos, p->eflag, n);
   KV_LAUNCHED();
   return 0;
 }

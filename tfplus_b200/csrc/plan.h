@@ -11,7 +11,7 @@ namespace kvhbm {
 //   uniq[r], counts[r]      distinct ids in first-occurrence order and how often each occurs
 //   idx[i]                  rank of position i's id
 //   pos[seg_off[r] + k]     k-th position holding uniq[r], increasing in k
-//   heavy[0 .. *heavy_n)    ranks with more than heavy_t occurrences
+//   heavy[0 .. *heavy_n)    ranks with more than heavy_t occurrences (eflag marks their entries of pos)
 //   first[r]                position of the first occurrence of uniq[r] (= pos[seg_off[r]])
 //   hint[r]                 {slot, ctl} of uniq[r] in the value table as the lookup of this
 //                           batch left them ({0xffffffff, 0} = unknown: consumers probe)
@@ -26,8 +26,13 @@ struct PlanView {
   const int* heavy_n;
   const int* first;
   uint2* hint;
+  const unsigned char* eflag;  // [n] 1 where pos[e] belongs to a heavy id
+  float* staged;          // [sum_dim / 32][staged_units][32][4]: occurrence rows of the heavy ids
+                          // in list order (written by the apply's staging pass, apply_plan.cu)
+  long long staged_units; // 512-byte units per 32-column part
   float* heavy_sum;       // [heavy_cap][sum_dim] gradient sums of the heavy ids
   unsigned* heavy_done;   // [heavy_cap] arrival counters, left at zero by every launch
+  unsigned* work;         // {next light group, blocks finished}, left at zero by every launch
   int heavy_t;
   int heavy_cap;
   int sum_dim;
