@@ -71,11 +71,13 @@ def init_table(dim):
 
 def algorithmic_bytes(b, u, d):
   """SURVEY.md 8(d) / BASELINE.md 3 per-stage algorithmic bytes."""
+  seg = b * (4 * d + 4) + 4 * d * u
+  app = (8 + 2 * 12 + 4 * d + 2 * 4 * d + 2 * 3 * 4 * d) * u
   return {
       "gather": (8 + 12 + 4 + 4 * d + 4 * d) * b,
       "unique": 8 * b + 8 * u + 4 * b,
-      "segment_sum": b * (4 * d + 4) + 4 * d * u,
-      "apply": (8 + 2 * 12 + 4 * d + 2 * 4 * d + 2 * 3 * 4 * d) * u,
+      # one fused pass here; the survey's figures for the two ops it replaces, added
+      "segment_sum+apply": seg + app,
   }
 
 
@@ -198,6 +200,21 @@ def main_reference(args):
   return 0
 
 
+def schedule_text(world, pipelined, K):
+  if not pipelined:
+    return "one CUDA graph per step, nothing runs ahead"
+  split = "CUDA graphs of %d steps; %d of the timed steps ran that way and %d strictly" % (
+      N_BATCHES, K - K % N_BATCHES, K % N_BATCHES)
+  if world > 1:
+    return ("sharded: lookup(t) -> barrier B -> expand -> local gradient sums -> gradient "
+            "exchange -> barrier C -> owner sum + apply(t) -> lookup(t+1); only the "
+            "requester-side dedup + id exchange, barrier A and the owner-side dedup of step t+1 "
+            "(functions of the ids alone) run beside step t; " + split)
+  return ("gather(t) -> [segment_sum + apply](t) -> gather(t+1) on one stream (the gradient "
+          "depends on the gathered rows, the next lookup on the apply); only the dedup plan of "
+          "batch t+1 (a function of its ids alone) is built beside step t; " + split)
+
+
 def workload_config(args, n_gpus):
   return {
       "workload": "KvVariable microbench: %d-key int64 table per GPU x %d GPU(s), dim %d, batch %d "
@@ -240,8 +257,7 @@ def main_ours(args):
   keys, B, D = args.keys, args.batch, args.dim
 
   if world > 1:
-    from tfplus_b200 import sharded
-    stepper = sharded.ShardedStepper(keys, D, B, HP, dev, rank, world)
+    stepper = ShardedStepper(keys, D, B, HP, dev, rank, world)
   else:
     stepper = LocalStepper(keys, D, B, dev)
   note('created')
@@ -313,7 +329,8 @@ def main_ours(args):
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
       sms = float(tt.item())
     strict = {"ms_per_step": sms / K, "value": B * world * K / (sms * 1e-3), "unit": UNIT,
-              "note": "one CUDA graph per step, step t+1 starts when step t has finished"}
+              "note": "plan -> lookup -> apply of one batch per CUDA graph; nothing of batch t+1 "
+                      "(not even its dedup plan) starts before step t has finished"}
 
   # ---- per-stage device times (same steps, events between the stages) ----
   note('timed %.3f ms/step' % (ms / K))
@@ -344,6 +361,11 @@ def main_ours(args):
   e2e_val = B * world * K / (e2e_ms * 1e-3)
   note('e2e')
 
+  check = None
+  if not args.no_check:
+    check = parity_check(world, rank, dev, dist)
+    note('parity check')
+
   if rank == 0:
     peaks = {}
     try:
@@ -353,44 +375,44 @@ def main_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
     ab = algorithmic_bytes(B, u_meas, D)
+    step_bytes = sum(ab.values())      # per GPU: every rank does the single-GPU step on its shard
     if world > 1:
-      # every rank does the single-GPU step's table traffic on its shard
-      ab = {"step": sum(ab.values()) * world}
+      ab = {"step": step_bytes}
       stage_ms = dict(stage_ms, step=ms / K)
     kern = {}
     for name, t_ms in stage_ms.items():
       if name in ab and t_ms > 0:
         kern[name] = {"ms": t_ms, "algorithmic_bytes": ab[name],
                       "achieved_gbs": ab[name] / (t_ms * 1e-3) / 1e9,
-                      "frac": ab[name] / (t_ms * 1e-3) / 1e9 / peak}
-    # the dominant KERNEL: stages are 1 (gather, apply), 2 (zero + segment-sum) or 3 (unique)
-    # launches, so compare per-launch time, not stage time
-    for name in kern:
-      kern[name]["launches"] = STAGE_LAUNCHES.get(name, 1)
-    top = max((k for k in kern), key=lambda k: kern[k]["ms"] / kern[k]["launches"]) if kern else None
+                      "frac": ab[name] / (t_ms * 1e-3) / 1e9 / peak,
+                      "launches": STAGE_LAUNCHES.get(name, 1)}
+    # the dominant kernel = the stage with the longest launch (the fused apply's staging pass is
+    # a fraction of its stage, so the stage time is charged to the main kernel: conservative)
+    top = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
     roof = None
     if top:
+      tr = measured_traffic(top)
       roof = {"bound": "hbm", "kernel": top, "achieved": kern[top]["achieved_gbs"], "peak": peak,
-              "unit": "GB/s", "frac": kern[top]["frac"], "traffic": TRAFFIC.get(top),
+              "unit": "GB/s", "frac": kern[top]["frac"],
+              "traffic": tr["bytes"] if tr else None, "traffic_source": tr,
               "peak_source": peak_src, "stages": kern,
-              "step_algorithmic_bytes": sum(ab.values()),
-              "step_frac_of_peak": sum(ab.values()) / (ms / K * 1e-3) / 1e9 / peak,
-              "step_frac_of_8TBs": sum(ab.values()) / (ms / K * 1e-3) / 1e9 / 8000.0}
+              "step_algorithmic_bytes_per_gpu": step_bytes,
+              "step_frac_of_peak": step_bytes / (ms / K * 1e-3) / 1e9 / peak,
+              "step_frac_of_8TBs": step_bytes / (ms / K * 1e-3) / 1e9 / 8000.0,
+              "note": "fractions are per GPU (one GPU's algorithmic bytes over one GPU's peak)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "unique_per_step": u_meas, "clocks": clk, "gpu_launches": int(launches),
         "host_enqueue_us_per_step": host_us,
-        "schedule": ("rotation graphs of %d steps with only the true dependencies between "
-                     "consecutive steps (dedup + gradient sum of batch t+1 run under the "
-                     "lookup/apply of batch t); remainder step by step" % N_BATCHES)
-                    if pipelined else "one CUDA graph per step",
+        "schedule": schedule_text(world, pipelined, K),
         "strict_per_step": strict,
         "e2e": {"value": e2e_val, "unit": UNIT,
                 "h2d_bytes_per_step": int(B * 8 + B * D * 4),
                 "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K},
         "roofline": roof,
+        "parity_check": check,
     }
     if world > 1:
       sent = stepper.padded.wire_bytes
@@ -398,12 +420,18 @@ def main_ours(args):
       if peer and stepper.padded.barrier_timeouts():
         raise SystemExit("peer barrier timed out %d times: the step is invalid"
                          % stepper.padded.barrier_timeouts())
+      # bytes that actually cross NVLink per GPU and step: the unique ids + counts
+      # routed to OTHER ranks, their rows back and their gradient sums out
+      u_remote = u_meas * (world - 1) / world
+      actual = int(u_remote * (12 + 2 * 4 * D))
       line["nvlink"] = {"exchange": "peer-memory stores fused into the producing kernels + "
-                                    "2 barrier kernels" if peer else "NCCL all_to_all_single x3",
-                        "bytes_sent_per_gpu_per_step": sent,
-                        "bus_gbs_per_gpu": sent / (ms / K * 1e-3) / 1e9,
+                                    "3 barrier kernels" if peer else "NCCL all_to_all_single x3",
+                        "bytes_sent_per_gpu_per_step": actual,
+                        "bus_gbs_per_gpu": actual / (ms / K * 1e-3) / 1e9,
+                        "frac_of_nvlink_peak": actual / (ms / K * 1e-3) / 1e9 / 900.0,
+                        "capacity_bytes_per_gpu_per_step": sent,
                         "peak_gbs_per_direction": 900.0, "measured_peer_copy_gbs": 770.0,
-                        "exchanges_per_step": 3, "barriers_per_step": 2 if peer else None,
+                        "exchanges_per_step": 3, "barriers_per_step": 3 if peer else None,
                         "capacity_per_peer": stepper.padded.cap,
                         "overflowed": stepper.padded.overflowed(),
                         "note": "fixed-capacity exchange of {id, occurrence count} pairs, rows, "
@@ -417,32 +445,54 @@ def main_ours(args):
       line["cpu_baseline"] = {
           "value": v, "unit": UNIT, "cores": cores, "kind": "port",
           "sample": "same workload (%d-key table), %d timed steps of B=%d after 2 warm-up, "
-                    "oracle port of the reference algorithm, %d threads" % (keys, cs, B, cores)}
+                    "oracle port of the reference algorithm, %d threads (the port's per-shard "
+                    "locking does not scale past ~16 threads: 32 cores measured slower than 16, "
+                    "so this is a stated baseline, not a tuned one)" % (keys, cs, B, cores)}
     emit_json(line)
+  failed = check is not None and not check["ok"]
   if world > 1:
     stepper.release()      # captured NCCL work must be gone before the process group
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
-  return 0
+  return 1 if failed else 0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full
-# captures of round 1 (profiles/r01_ncu_kernels.txt); None where no capture exists
-STAGE_LAUNCHES = {"gather": 1, "unique": 3, "segment_sum": 2, "apply": 1, "step": 1}
-TRAFFIC = {"apply": 31.52e6, "gather": 8.33e6, "segment_sum": 22.23e6, "unique": 4.3e6}
+# kernels of this library per stage (the fused apply is the staging pass + the chain/apply kernel)
+STAGE_LAUNCHES = {"gather": 1, "unique": 5, "segment_sum+apply": 2, "step": 1}
+
+
+def measured_traffic(kernel):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, as the last committed
+  `ncu --set full` capture recorded it (profiles/ncu_traffic.json, written by
+  scripts/ncu_summary.py --json together with the git revision it was taken at); None when no
+  capture of this kernel exists."""
+  try:
+    d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    k = d["kernels"].get(kernel)
+    return None if k is None else {"bytes": k["dram_bytes"], "git": d.get("git"), "kernel": k.get("name")}
+  except Exception:
+    return None
 
 
 class LocalStepper:
-  """One GPU: var + m_v_linear tables and the four-stage step.
+  """One GPU: var + m_v_linear tables and the step  plan -> lookup -> fused gradient sum + apply.
 
-  The optimizer's scalar inputs live in device memory (`hp`, as TF would hand them to a GPU
-  kernel) and beta^t is advanced on the device by every apply launch (TF Adam's `_finish`), so
-  whole steps are capturable: the timed loops replay CUDA graphs (one per rotation of the
-  batches, or one per step) instead of paying ~10 host launches per step.
+  plan    kv_plan_build: tf.unique_with_counts of the batch's ids + occurrence lists.  It is a
+          function of the ids ALONE, so the input pipeline may build it ahead of the step.
+  gather  kv_gather_or_insert_plan: KvVariableGatherOrInsertV2 over all B ids.
+  apply   kv_apply_plan_dev: UnsortedSegmentSum (TF's order, bit-exact) + GroupAdam v4 in one
+          pass, beta^t advanced in the same launch (TF Adam's `_finish`).
+
+  The gradient of a real model is a function of the gathered rows, so the apply of a batch may
+  not start before its lookup has finished; the lookup of the next batch reads what this apply
+  wrote.  gather(t) -> apply(t) -> gather(t+1) is therefore ONE chain on one stream, in every
+  schedule timed here.  Only plan(t+1) runs beside it (second stream).  The optimizer's scalar
+  inputs live in device memory (`hp`), so steps are capturable and the timed loops replay CUDA
+  graphs.
   """
 
-  STAGES = ["gather", "unique", "segment_sum", "apply"]
+  STAGES = ["unique", "gather", "segment_sum+apply"]
 
   def __init__(self, keys, dim, batch, dev):
     import torch
@@ -457,10 +507,8 @@ class LocalStepper:
     self.hp = torch.tensor([HP["lr"], HP["beta1"], HP["beta2"], HP["beta1"], HP["beta2"],
                             HP["epsilon"], HP["l1"], HP["l2"], HP["l21"]], dtype=torch.float32,
                            device=dev)
-    self.graphs = {}
-    self.overlap = os.environ.get("KVHBM_BENCH_OVERLAP", "1") != "0"
     self.side = torch.cuda.Stream(device=dev)
-    self.side2 = torch.cuda.Stream(device=dev)
+    self.lookahead = os.environ.get("KVHBM_BENCH_PLAN_AHEAD", "1") != "0"
 
   def populate(self):
     torch, ops = self.torch, self.ops
@@ -471,56 +519,20 @@ class LocalStepper:
     torch.cuda.synchronize()
 
   # ---- the step, stage by stage (eager; also what gets captured) ----
-  def new_buffers(self):
-    t, B, D, dev = self.torch, self.batch, self.dim, self.dev
-    return {"rows": t.empty((B, D), dtype=t.float32, device=dev),
-            "uniq": t.empty(B, dtype=t.int64, device=dev),
-            "idx": t.empty(B, dtype=t.int32, device=dev),
-            "num": t.zeros(1, dtype=t.int32, device=dev),
-            "gsum": t.empty((B, D), dtype=t.float32, device=dev)}
+  def stage(self, name, ids, grad, plan, rows):
+    ops = self.ops
+    if name == "unique":
+      plan.build(ids)
+    elif name == "gather":
+      ops.kv_variable_gather_or_insert_plan(self.var, plan, out=rows)
+    elif name == "segment_sum+apply":
+      ops.kv_variable_apply_plan(ops.OPT_GROUP_ADAM_V4, self.var, self.slot, None, plan, grad,
+                                 self.hp, advance_powers=True)
 
-  def stage(self, name, ids, grad, buf):
-    ops, lib, C = self.ops, self.ops._lib.load(), self.ops.check
-    st = self.torch.cuda.current_stream(self.dev).cuda_stream
-    if name == "gather":
-      ops.kv_variable_gather_or_insert_v2(self.var, ids, out=buf["rows"])
-    elif name == "unique":
-      ws = ops.Workspace.get(self.dev)
-      C(lib.kv_unique(ws.ptr, ids.data_ptr(), ids.numel(), buf["uniq"].data_ptr(),
-                      buf["idx"].data_ptr(), None, buf["num"].data_ptr(), st))
-    elif name == "zero":
-      ops.zero_rows(buf["gsum"])
-    elif name == "segment_sum":
-      ops.unsorted_segment_sum(grad, buf["idx"], buf["num"], out=buf["gsum"],
-                               accumulate=self.overlap)
-    elif name == "apply":
-      # beta1_power *= beta1, beta2_power *= beta2 happen in the same launch (last block)
-      ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, buf["gsum"], buf["uniq"],
-                                                     self.hp, num_indices=buf["num"],
-                                                     advance_powers=True)
-
-  def step_eager(self, ids, grad, buf):
-    """gather and (unique -> segment_sum) only depend on the ids / gradients, so they run on
-    two streams and join before the apply (the fork/join is captured into the step graph)."""
-    torch = self.torch
-    if not self.overlap:
-      for name in self.STAGES:
-        self.stage(name, ids, grad, buf)
-      return buf["rows"]
-    # (the eager warm-up also goes through here, so the side streams exist before capture)
-    main = torch.cuda.current_stream(self.dev)
-    self.side.wait_stream(main)
-    self.side2.wait_stream(main)
-    with torch.cuda.stream(self.side2):
-      self.stage("zero", ids, grad, buf)       # the sums' destination, off the critical path
-    with torch.cuda.stream(self.side):
-      self.stage("unique", ids, grad, buf)
-      self.side.wait_stream(self.side2)
-      self.stage("segment_sum", ids, grad, buf)
-    self.stage("gather", ids, grad, buf)
-    main.wait_stream(self.side)
-    self.stage("apply", ids, grad, buf)
-    return buf["rows"]
+  def step_eager(self, ids, grad, plan, rows):
+    for name in self.STAGES:
+      self.stage(name, ids, grad, plan, rows)
+    return rows
 
   def _capture(self, fn):
     torch = self.torch
@@ -530,64 +542,63 @@ class LocalStepper:
     return g
 
   def prepare(self, ids_d, grads_d):
-    """Warm every batch once eagerly (sizes the workspace, no allocation later), then capture
-    one full-step graph and four single-stage graphs per batch."""
+    """Warm every batch once eagerly (sizes every scratch buffer, no allocation later), then
+    capture: one graph per strict step, one per stage and batch, and the rotation."""
+    torch, ops = self.torch, self.ops
     self.ids_d, self.grads_d = ids_d, grads_d
-    self.bufs = [self.new_buffers() for _ in ids_d]
-    l0 = self.ops._lib.launch_count()
-    for ids, grad, buf in zip(ids_d, grads_d, self.bufs):
-      self.step_eager(ids, grad, buf)
-    # kernels of this library per step (the beta^t advance is inside the apply launch)
-    self.launches_per_step = (self.ops._lib.launch_count() - l0) // len(ids_d)
-    self.torch.cuda.synchronize()
+    n = len(ids_d)
+    self.plans = [ops.Plan(self.batch, self.dev) for _ in range(n)]
+    self.rows = [torch.empty((self.batch, self.dim), dtype=torch.float32, device=self.dev)
+                 for _ in range(n)]
+    l0 = ops._lib.launch_count()
+    for i in range(n):
+      self.step_eager(ids_d[i], grads_d[i], self.plans[i], self.rows[i])
+    self.launches_per_step = (ops._lib.launch_count() - l0) // n
+    torch.cuda.synchronize()
     # captured work may not grow the tables: make the room now (also refreshes the exact counts)
-    self.ops.kv_variable_reserve(self.var, 2 * self.batch)
-    self.ops.kv_variable_reserve(self.slot, 2 * self.batch)
-    self.full = [self._capture(lambda i=i: self.step_eager(ids_d[i], grads_d[i], self.bufs[i]))
-                 for i in range(len(ids_d))]
-    def one_stage(n, i):
-      if n == "segment_sum" and self.overlap:   # timed alone it includes its zeroing pass
-        self.stage("zero", ids_d[i], grads_d[i], self.bufs[i])
-      self.stage(n, ids_d[i], grads_d[i], self.bufs[i])
+    ops.kv_variable_reserve(self.var, 2 * self.batch)
+    ops.kv_variable_reserve(self.slot, 2 * self.batch)
+    self.full = [self._capture(lambda i=i: self.step_eager(ids_d[i], grads_d[i], self.plans[i],
+                                                           self.rows[i])) for i in range(n)]
     self.stage_graphs = {
-        n: [self._capture(lambda i=i, n=n: one_stage(n, i)) for i in range(len(ids_d))]
-        for n in self.STAGES}
-    self.rotation = None
-    if self.overlap and os.environ.get("KVHBM_BENCH_PIPELINE", "1") != "0":
-      self.rotation = self._capture(self.rotation_eager)
-    self.torch.cuda.synchronize()
+        name: [self._capture(lambda i=i, name=name: self.stage(name, ids_d[i], grads_d[i],
+                                                               self.plans[i], self.rows[i]))
+               for i in range(n)] for name in self.STAGES}
+    self.rotation = self._capture(self.rotation_eager) if self.lookahead else None
+    if self.rotation is not None:
+      self.plans[0].build(ids_d[0])   # the rotation expects the plan of its first batch
+    torch.cuda.synchronize()
 
   def step(self, i):
+    """Strict: plan -> lookup -> apply of one batch, nothing of the next batch before it ends."""
     self.full[i % len(self.full)].replay()
 
   def rotation_eager(self):
-    """All rotating batches, in order, with only the TRUE dependencies between consecutive
-    steps: lookup(t+1) and apply(t+1) wait for apply(t) (they read what it wrote), the dedup
-    and gradient sum of batch t+1 depend on nothing but their inputs, so they run under the
-    lookup/apply of batch t.  Same kernels, same table updates in the same order as step by
-    step (tests/test_gpu_fullsize.py compares the two, and both with the oracle)."""
+    """All rotating batches in order.  Main stream: gather(t) -> apply(t) -> gather(t+1) ...
+    (the dependency chain of a training loop).  Second stream: the plan of batch t+1 — a
+    function of its ids alone — is built while batch t trains; the rotation ends by building
+    the plan of batch 0 for the next replay."""
     torch = self.torch
     main = torch.cuda.current_stream(self.dev)
-    s_u, s_s = self.side, self.side2
-    s_u.wait_stream(main)
-    s_s.wait_stream(main)
-    for ids, grad, buf in zip(self.ids_d, self.grads_d, self.bufs):
-      with torch.cuda.stream(s_s):
-        self.stage("zero", ids, grad, buf)
-      with torch.cuda.stream(s_u):             # one dedup scratch per device: a chain
-        self.stage("unique", ids, grad, buf)
-        ev_u = torch.cuda.Event()
-        ev_u.record(s_u)
-      with torch.cuda.stream(s_s):
-        s_s.wait_event(ev_u)
-        self.stage("segment_sum", ids, grad, buf)
-        ev_s = torch.cuda.Event()
-        ev_s.record(s_s)
-      self.stage("gather", ids, grad, buf)     # after apply(t-1): stream order
-      main.wait_event(ev_s)
-      self.stage("apply", ids, grad, buf)
-    main.wait_stream(s_u)
-    main.wait_stream(s_s)
+    side = self.side
+    n = len(self.ids_d)
+    side.wait_stream(main)
+    ev_plan, ev_apply = [None] * n, [None] * n
+    for t in range(n):
+      if t > 0:
+        main.wait_event(ev_plan[t])               # plan(t) was built beside step t-1
+      self.stage("gather", self.ids_d[t], self.grads_d[t], self.plans[t], self.rows[t])
+      self.stage("segment_sum+apply", self.ids_d[t], self.grads_d[t], self.plans[t], self.rows[t])
+      ev_apply[t] = torch.cuda.Event()
+      ev_apply[t].record(main)
+      nxt = (t + 1) % n
+      with torch.cuda.stream(side):
+        if nxt == 0:
+          side.wait_event(ev_apply[0])            # the last reader of plan(0)'s buffers
+        self.stage("unique", self.ids_d[nxt], None, self.plans[nxt], None)
+        ev_plan[nxt] = torch.cuda.Event()
+        ev_plan[nxt].record(side)
+    main.wait_stream(side)
 
   def run_steps(self, K):
     """K consecutive steps: whole rotations as one graph each, the rest step by step."""
@@ -599,6 +610,8 @@ class LocalStepper:
     while i < K:
       self.full[i % n].replay()
       i += 1
+    if self.rotation is not None and K % n:
+      self.plans[0].build(self.ids_d[0])          # leave the state a rotation expects
 
   def stage_times(self, steps):
     """Average device time of each stage: K back-to-back replays of that stage's graph over the
@@ -625,13 +638,15 @@ class LocalStepper:
     copies the gathered rows back.  The three legs run on three streams, double-buffered, so
     the H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i (PCIe is full
     duplex); every copy still happens, once per step, inside the timed region."""
-    t = self.torch
+    t, ops = self.torch, self.ops
     self.ids_h, self.grads_h, self.rows_h = ids_h, grads_h, rows_h
     self.s_h2d, self.s_d2h = t.cuda.Stream(device=self.dev), t.cuda.Stream(device=self.dev)
     self.h_ids = [t.empty(self.batch, dtype=t.int64, device=self.dev) for _ in range(2)]
     self.h_grad = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
                    for _ in range(2)]
-    self.h_buf = [self.new_buffers() for _ in range(2)]
+    self.h_plan = [ops.Plan(self.batch, self.dev) for _ in range(2)]
+    self.h_rows = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                   for _ in range(2)]
     self.rows_host = [rows_h, t.empty_like(rows_h).pin_memory()]
     self.ev_in = [t.cuda.Event() for _ in range(2)]     # inputs of slot k are on the device
     self.ev_done = [t.cuda.Event() for _ in range(2)]   # kernels of slot k finished
@@ -639,10 +654,11 @@ class LocalStepper:
     for k in range(2):
       self.h_ids[k].copy_(ids_h[k])
       self.h_grad[k].copy_(grads_h[k])
-      self.step_eager(self.h_ids[k], self.h_grad[k], self.h_buf[k])
+      self.step_eager(self.h_ids[k], self.h_grad[k], self.h_plan[k], self.h_rows[k])
     t.cuda.synchronize()
     self.e2e = [self._capture(lambda k=k: self.step_eager(self.h_ids[k], self.h_grad[k],
-                                                          self.h_buf[k])) for k in range(2)]
+                                                          self.h_plan[k], self.h_rows[k]))
+                for k in range(2)]
     main = t.cuda.current_stream(self.dev)
     for k in range(2):
       self.ev_done[k].record(main)
@@ -666,13 +682,323 @@ class LocalStepper:
     self.ev_done[k].record(main)
     with t.cuda.stream(self.s_d2h):
       self.s_d2h.wait_event(self.ev_done[k])
-      self.rows_host[k].copy_(self.h_buf[k]["rows"], non_blocking=True)
+      self.rows_host[k].copy_(self.h_rows[k], non_blocking=True)
       self.ev_out[k].record(self.s_d2h)
 
   def finish_host(self):
     main = self.torch.cuda.current_stream(self.dev)
     main.wait_stream(self.s_h2d)
     main.wait_stream(self.s_d2h)
+
+
+class ShardedStepper:
+  """Weak-scaling microbench: `keys` keys per GPU, every rank brings its own batch."""
+
+  STAGES = ["route+lookup", "grads+apply"]
+
+  def __init__(self, keys_per_gpu, dim, batch, hp, dev, rank, world):
+    import torch
+    from tfplus_b200 import ops, sharded
+    self.torch, self.ops, self.sharded = torch, ops, sharded
+    self.keys, self.dim, self.batch, self.dev = keys_per_gpu, dim, batch, dev
+    self.rank, self.world, self.hp = rank, world, hp
+    cap = int(keys_per_gpu * 1.15) + batch
+    self.tbl = sharded.ShardedKvVariable(dim, world, rank, dev, slot_dims=(3 * dim,),
+                                 capacity_hint=cap, seed=1)
+    self.ops.init_kv_variable_v2(self.tbl.var, torch.from_numpy(init_table(dim)).to(dev))
+    self.ops.init_kv_variable_v2(self.tbl.slots[0], torch.zeros(INIT_ROWS, 3 * dim, device=dev))
+    self.hpt = torch.tensor([hp["lr"], hp["beta1"], hp["beta2"], hp["beta1"], hp["beta2"],
+                             hp["epsilon"], hp["l1"], hp["l2"], hp["l21"]], dtype=torch.float32,
+                            device=dev)
+    self.betas = torch.tensor([hp["beta1"], hp["beta2"]], dtype=torch.float32, device=dev)
+    self.launches_per_step = 0
+    self.steps_done = 0
+
+  def populate(self):
+    """Insert the keys this rank owns out of the global id range [0, keys * world)."""
+    t = self.torch
+    total = self.keys * self.world
+    chunk = 1 << 20
+    for s in range(0, total, chunk):
+      ids = t.arange(s, min(total, s + chunk), dtype=t.int64, device=self.dev)
+      sorted_ids, _, counts = self.ops.partition_ids(ids, self.world, "hash")
+      c = counts.cpu().tolist()
+      lo = sum(c[:self.rank])
+      mine = sorted_ids[lo:lo + c[self.rank]]
+      if mine.numel():
+        self.ops.kv_variable_gather_or_insert_v2(self.tbl.var, mine)
+        self.ops.kv_variable_gather_or_insert_v2(self.tbl.slots[0], mine)
+    t.cuda.synchronize()
+
+  def step_exact(self, ids, grad):
+    """The variable-size path (host reads the per-shard counts): reference behaviour for the
+    padded path and its fallback on overflow."""
+    rows = self.tbl.lookup(ids)
+    owner_ids, owner_grads = self.tbl.owner_gradients(grad)
+    if owner_ids.numel():
+      self.ops.kv_variable_group_sparse_apply_adam_v4_dev(self.tbl.var, self.tbl.slots[0], owner_grads,
+                                                     owner_ids, self.hpt)
+    self.hpt[1:3].mul_(self.betas)
+    return rows
+
+  def step_eager(self, ids, grad):
+    self.steps_done += 1
+    return self.padded.run(ids, grad)
+
+  def prepare(self, ids_d, grads_d):
+    from tfplus_b200 import _lib
+    t = self.torch
+    self.ids_d, self.grads_d = ids_d, grads_d
+    self.padded = self.sharded.make_padded_step(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
+                                   self.world, self.rank, self.dev, self.hpt, self.betas)
+    l0 = _lib.launch_count()
+    for i in range(2):
+      self.step_eager(ids_d[i], grads_d[i])
+    self.launches_per_step = (_lib.launch_count() - l0) // 2
+    t.cuda.synchronize()
+    if self.padded.overflowed():
+      raise RuntimeError("padded shard exchange overflowed: raise cap")
+    self.ops.kv_variable_reserve(self.tbl.var, 2 * self.padded.cap * self.world)
+    self.ops.kv_variable_reserve(self.tbl.slots[0], 2 * self.padded.cap * self.world)
+    self.graphs = [self._capture(lambda i=i: self.padded.run(ids_d[i], grads_d[i]))
+                   for i in range(len(ids_d))]
+    if self.graphs and self.graphs[0] is None:
+      self.graphs = []
+    # the pipelined schedule: one graph per rotation of the batches (PeerShardedStep only)
+    self.rotation = None
+    if (self.graphs and hasattr(self.padded, "run_rotation") and self.padded.fused_route
+        and len(ids_d) % 2 == 0 and os.environ.get("KVHBM_BENCH_PIPELINE", "1") != "0"):
+      self.padded.run_rotation(ids_d, grads_d)        # once eagerly: errors surface here
+      t.cuda.synchronize()
+      self.rotation = self._capture(lambda: self.padded.run_rotation(ids_d, grads_d))
+    t.cuda.synchronize()
+
+  def run_steps(self, K):
+    """K consecutive steps: whole rotations as one graph each, the rest step by step."""
+    n, i = len(self.ids_d), 0
+    if self.rotation is not None:
+      while K - i >= n:
+        self.rotation.replay()
+        i += n
+      self.steps_done += i
+    while i < K:
+      self.step(i)
+      i += 1
+
+  def step(self, i):
+    k = i % len(self.ids_d)
+    self.steps_done += 1
+    if self.graphs:
+      self.graphs[k].replay()
+      return self.padded.out
+    return self.padded.run(self.ids_d[k], self.grads_d[k])
+
+  def release(self):
+    self.graphs = []
+    self.e2e = []
+    self.rotation = None
+
+  def stage_times(self, steps):
+    t = self.torch
+    a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    t.cuda.synchronize()
+    a.record()
+    for i in range(steps):
+      self.step(i)
+    b.record()
+    t.cuda.synchronize()
+    return {"sharded step": a.elapsed_time(b) / steps}
+
+  def _capture(self, fn):
+    t = self.torch
+    if os.environ.get("KVHBM_SHARDED_GRAPH", "1") == "0":
+      return None
+    side = t.cuda.Stream(device=self.dev)
+    side.wait_stream(t.cuda.current_stream(self.dev))
+    with t.cuda.stream(side):
+      g = t.cuda.CUDAGraph()
+      with t.cuda.graph(g, stream=side):
+        fn()
+    t.cuda.current_stream(self.dev).wait_stream(side)
+    return g
+
+  def prepare_host(self, ids_h, grads_h, rows_h):
+    """End to end: every step copies its ids + gradients from pinned host memory and its rows
+    back.  Two input / output slots and two copy streams, so the H2D of step i+1 and the D2H
+    of step i-1 run under the kernels and exchanges of step i; every copy still happens once
+    per step inside the timed region."""
+    t = self.torch
+    self.ids_h, self.grads_h, self.rows_h = ids_h, grads_h, rows_h
+    self.s_h2d, self.s_d2h = t.cuda.Stream(device=self.dev), t.cuda.Stream(device=self.dev)
+    self.h_ids = [t.empty(self.batch, dtype=t.int64, device=self.dev) for _ in range(2)]
+    self.h_grad = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                   for _ in range(2)]
+    self.h_out = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
+                  for _ in range(2)]
+    self.rows_host = [rows_h, t.empty_like(rows_h).pin_memory()]
+    self.ev_in = [t.cuda.Event() for _ in range(2)]
+    self.ev_done = [t.cuda.Event() for _ in range(2)]
+    self.ev_out = [t.cuda.Event() for _ in range(2)]
+    for k in range(2):
+      self.h_ids[k].copy_(ids_h[k])
+      self.h_grad[k].copy_(grads_h[k])
+    t.cuda.synchronize()
+    self.e2e = [self._capture(lambda k=k: self.padded.run(self.h_ids[k], self.h_grad[k],
+                                                          out=self.h_out[k])) for k in range(2)]
+    main = t.cuda.current_stream(self.dev)
+    for k in range(2):
+      self.ev_done[k].record(main)
+      self.ev_out[k].record(main)
+    self.e2e_i = 0
+
+  def finish_host(self):
+    main = self.torch.cuda.current_stream(self.dev)
+    main.wait_stream(self.s_h2d)
+    main.wait_stream(self.s_d2h)
+
+  def step_host(self, i):
+    t = self.torch
+    k = self.e2e_i & 1
+    self.e2e_i += 1
+    j = i % len(self.ids_h)
+    main = t.cuda.current_stream(self.dev)
+    with t.cuda.stream(self.s_h2d):
+      self.s_h2d.wait_event(self.ev_done[k])       # slot k's previous step no longer reads it
+      self.h_ids[k].copy_(self.ids_h[j], non_blocking=True)
+      self.h_grad[k].copy_(self.grads_h[j], non_blocking=True)
+      self.ev_in[k].record(self.s_h2d)
+    main.wait_event(self.ev_in[k])
+    main.wait_event(self.ev_out[k])                # slot k's rows have been drained to the host
+    if self.e2e[k] is not None:
+      self.e2e[k].replay()
+    else:
+      self.padded.run(self.h_ids[k], self.h_grad[k], out=self.h_out[k])
+    self.steps_done += 1
+    self.ev_done[k].record(main)
+    with t.cuda.stream(self.s_d2h):
+      self.s_d2h.wait_event(self.ev_done[k])
+      self.rows_host[k].copy_(self.h_out[k], non_blocking=True)
+      self.ev_out[k].record(self.s_d2h)
+
+
+# ----------------------------------------------------------------------------- self-check
+def _check_batches(world, steps, keys, batch, dim):
+  """Deterministic small batches for the untimed parity check: 90 % uniform ids over the key
+  range, 10 % out of 64 hot keys (duplicates within and across ranks), N(0,1) gradients."""
+  out = []
+  for s in range(steps):
+    per_rank = []
+    for r in range(world):
+      g = np.random.Generator(np.random.PCG64(1000 * s + r + 17))
+      ids = g.integers(0, keys, size=batch, dtype=np.int64)
+      hot = g.random(batch) < 0.1
+      ids[hot] = (g.integers(0, 64, size=int(hot.sum()), dtype=np.int64) * 7919) % keys
+      per_rank.append((ids, g.standard_normal((batch, dim), dtype=np.float32)))
+    out.append(per_rank)
+  return out
+
+
+def parity_check(world, rank, dev, dist):
+  """Untimed correctness evidence for the path the timed loops run: a small replay (fresh
+  tables, same code path: strict steps, then the rotation schedule) whose final table state -
+  every shard exported and gathered on rank 0 - is compared with ONE oracle table fed the
+  concatenated batches: membership and frequency words bit-exactly, value and slot rows at
+  1e-6.  Returns the dict that goes into the JSON line (rank 0) or None."""
+  import torch
+  from tfplus_b200 import ops
+  keys_pg, B, D, steps = 20000, 2048, DIM, 6
+  keys = keys_pg * world
+  data = _check_batches(world, steps, keys, B, D)
+  ids_d = [torch.from_numpy(data[s][rank][0]).to(dev) for s in range(steps)]
+  grads_d = [torch.from_numpy(data[s][rank][1]).to(dev) for s in range(steps)]
+  if world > 1:
+    st = ShardedStepper(keys_pg, D, B, HP, dev, rank, world)
+    st.populate()
+    st.padded = st.sharded.make_padded_step(st.tbl.var, st.tbl.slots[0], D, B, world, rank, dev,
+                                            st.hpt, st.betas)
+    var, slot = st.tbl.var, st.tbl.slots[0]
+    for s in range(2):
+      st.padded.run(ids_d[s], grads_d[s])
+    if hasattr(st.padded, "run_rotation") and st.padded.fused_route:
+      st.padded.run_rotation(ids_d[2:], grads_d[2:])
+      path = "PeerShardedStep.run x2 + run_rotation x%d" % (steps - 2)
+    else:
+      for s in range(2, steps):
+        st.padded.run(ids_d[s], grads_d[s])
+      path = "%s.run x%d" % (type(st.padded).__name__, steps)
+    rows_last = st.padded.out.cpu().numpy().copy()
+    torch.cuda.synchronize()
+    bad = st.padded.overflowed() or (hasattr(st.padded, "barrier_timeouts")
+                                     and st.padded.barrier_timeouts() > 0)
+  else:
+    st = LocalStepper(keys, D, B, dev)
+    st.populate()
+    var, slot = st.var, st.slot
+    plan = ops.Plan(B, dev)
+    rows = torch.empty((B, D), dtype=torch.float32, device=dev)
+    for s in range(steps):
+      st.step_eager(ids_d[s], grads_d[s], plan, rows)
+    rows_last = rows.cpu().numpy().copy()
+    path = "plan -> gather_or_insert_plan -> apply_plan x%d" % steps
+    bad = False
+  exp = {}
+  for name, tb in (("var", var), ("slot", slot)):
+    k, v, _, bl, fk, fv = ops.kv_variable_export(tb, first_n=6, enable_cutoff=False,
+                                                 freq_dtype=torch.int32)
+    exp[name] = [x.cpu().numpy() for x in (k, v, bl, fk, fv)]
+  payload = (exp, bool(bad))
+  if world > 1:
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+  else:
+    gathered = [payload]
+  if rank != 0:
+    return None
+  from oracle import binding as ob
+  o_var = ob.OracleTable(D, 0, seed=1)
+  o_slot = ob.OracleTable(3 * D, 0, seed=1)
+  o_var.set_init_table(init_table(D))
+  o_slot.set_init_table(np.zeros((INIT_ROWS, 3 * D), np.float32))
+  all_ids = np.arange(keys, dtype=np.int64)
+  o_var.gather_or_insert(all_ids, today=TODAY)
+  o_slot.gather_or_insert(all_ids, today=TODAY)
+  b1p, b2p = np.float32(HP["beta1"]), np.float32(HP["beta2"])
+  want_rows = None
+  for s in range(steps):
+    ids = np.concatenate([data[s][r][0] for r in range(world)])
+    grad = np.concatenate([data[s][r][1] for r in range(world)])
+    want_rows = o_var.gather_or_insert(ids, today=TODAY)
+    u, idx = ob.unique(ids)
+    ob.apply_group_adam_v4(o_var, o_slot, u, ob.segment_sum(grad, idx, u.size), HP["lr"],
+                           float(b1p), float(b2p), HP["beta1"], HP["beta2"], HP["epsilon"],
+                           HP["l1"], HP["l2"], HP["l21"], today=TODAY)
+    b1p, b2p = b1p * np.float32(HP["beta1"]), b2p * np.float32(HP["beta2"])
+  res = {"ok": True, "keys": keys, "steps": steps, "batch_per_gpu": B, "path": path,
+         "compared": "membership, blacklist and frequency words bit-exact; value and slot rows "
+                     "rtol 1e-6 atol 1e-7; rank 0's looked-up rows of the last step",
+         "against": "one oracle table fed the concatenated batches"}
+  try:
+    assert not any(g[1] for g in gathered), "exchange overflow or barrier timeout"
+    np.testing.assert_allclose(rows_last, want_rows[:B].reshape(B, D), rtol=1e-6, atol=1e-7)
+    for name, otab in (("var", o_var), ("slot", o_slot)):
+      ref = otab.export(first_n=6, enable_cutoff=False, freq_u32=True)
+      rows, freq, black = {}, {}, set()
+      for g in gathered:
+        k, v, bl, fk, fv = g[0][name]
+        rows.update({int(a): b for a, b in zip(k, v)})
+        freq.update({int(a): int(b) for a, b in zip(fk, fv.view(np.uint32))})
+        black.update(int(a) for a in bl)
+      assert freq == {int(a): int(b) for a, b in zip(ref["freq_keys"], ref["freq_values"])}, \
+          name + ": frequency words differ"
+      assert black == set(int(a) for a in ref["blacklist"]), name + ": blacklists differ"
+      assert set(rows) == set(int(a) for a in ref["keys"]), name + ": key sets differ"
+      got = np.stack([rows[int(a)] for a in ref["keys"]])
+      np.testing.assert_allclose(got, ref["values"].reshape(got.shape), rtol=1e-6, atol=1e-7,
+                                 err_msg=name + " rows")
+  except AssertionError as e:
+    res["ok"] = False
+    res["error"] = str(e)[:400]
+  return res
 
 
 class _QuietStdout:
@@ -713,6 +1039,7 @@ def main():
   ap.add_argument("--batch", type=int, default=BATCH)
   ap.add_argument("--dim", type=int, default=DIM)
   ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+  ap.add_argument("--no-check", action="store_true", help="skip the untimed parity self-check")
   args = ap.parse_args()
   if args.impl == "reference":
     return main_reference(args)

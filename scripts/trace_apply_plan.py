@@ -34,13 +34,13 @@ ops.kv_variable_apply_plan(ops.OPT_GROUP_ADAM_V4, st.var, st.slot, None, plan, g
                            advance_powers=True)
 torch.cuda.synchronize()
 lib.kv_debug_set_trace(None)
-t = tb.cpu().numpy().reshape(-1, 4)
-nw = 10
+raw = tb.cpu().numpy()
+t = raw.reshape(-1, 4)
+nw = 20
 t = t[: (len(t) // nw) * nw]
 live = t[:, 0] > 0
 t0 = t[live, 0].min()
-start, heavy, end, groups = t[:, 0] - t0, t[:, 1] - t0, t[:, 2] - t0, t[:, 3].copy()
-groups.reshape(-1, nw)[:, 0] = 0
+start, heavy, end, groups = t[:, 0] - t0, t[:, 1] - t0, t[:, 2] - t0, t[:, 3]
 pc = lambda a: np.percentile(a, [0, 10, 50, 90, 100]).round()
 print("warps", live.sum(), "span ns", end[live].max())
 print("start:", pc(start[live])); print("heavy done:", pc(heavy[live])); print("end:", pc(end[live]))
@@ -48,8 +48,7 @@ print("light dur:", pc((end - heavy)[live])); print("groups/warp:", pc(groups[li
 print("per light group ns:", pc(((end - heavy) / np.maximum(groups, 1))[live & (groups > 0)]))
 hb = (heavy - start)[live].reshape(-1, nw)[:, 0]
 order = np.argsort(-hb)[:12]
-wc = t[:, 3].reshape(-1, nw)[:, 0]
-print("longest heavy phases (block, ns, wait+add(b) cycles, chain cycles):", [(int(b), int(hb[b]), int(wc[b] & 0xffffffff), int(wc[b] >> 32)) for b in order])
+print("longest heavy phases (block, ns):", [(int(b), int(hb[b])) for b in order])
 uniq, idx, counts, num, seg_off, pos = plan.arrays()
 c = counts[: int(num[0])].cpu().numpy()
 print("U", c.size, "max count", c.max(), "heavy ids", (c > 32).sum(), "heavy occ", c[c > 32].sum())

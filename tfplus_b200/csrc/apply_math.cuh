@@ -384,6 +384,13 @@ struct GradSrc {
   int heavy_t;
   const uint2* hint;     // {slot, ctl} of id i in the value table as this batch's lookup left it, or null
   bool cg;               // dense rows were written by other SMs during this launch: read at L2
+  // dense rows produced DURING this launch (the heavy ids of the planned kernel): id i of the
+  // group is ids[remap[i]], its gradient row `i` (gstride floats apart) may be read once
+  // ready[i] has reached ready_n; the reader puts the counter back to zero
+  const int* remap = nullptr;
+  unsigned* ready = nullptr;
+  unsigned ready_n = 0;
+  int gstride = 0;
 };
 
 template <int NW, int VEC, int CPL>
@@ -436,7 +443,8 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   uint32_t a_old = 0, b_old = 0;
   int gcnt = 1, goff = 0;
   bool mine = valid;
-  if (valid) key = ids[i];
+  const long long ii = (valid && gs.remap) ? (long long)gs.remap[i] : i;   // index into ids / hint
+  if (valid) key = ids[ii];
   if (valid && planned) {
     gcnt = gs.counts[i];
     goff = gs.seg_off[i];
@@ -448,7 +456,7 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
     Slot sv, ssa, ssb, x0, x1, y0, y1, z0, z1;
     long long hpos = -1;
     if (gs.hint) {
-      const uint32_t h = gs.hint[i].x;
+      const uint32_t h = gs.hint[ii].x;
       if (h != 0xffffffffu && (unsigned long long)h <= var.mask) hpos = (long long)h;
     }
     if (hpos >= 0) x0 = load_slot(var.slots + hpos);
@@ -556,7 +564,14 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
           }
         }
         if (!planned) {
-          const float* gp = gs.grad + (base + kl - gs.row0) * (long long)dim;
+          const long long gi = base + kl - gs.row0;
+          if (gs.ready && gi < n - gs.row0) {
+            // the sum is being produced by a chain of this launch: the value and slot rows are
+            // already in flight, wait here
+            while (*reinterpret_cast<volatile unsigned*>(gs.ready + gi) < gs.ready_n) __nanosleep(100);
+            __threadfence();
+          }
+          const float* gp = gs.grad + gi * (long long)(gs.gstride ? gs.gstride : dim);
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             const int off = (q * tpr + tl) * VEC;
@@ -665,6 +680,7 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
     }
   }
   __syncwarp();
+  if (gs.ready && valid) gs.ready[i - gs.row0] = 0u;   // every tile is past its wait
 }
 
 }  // namespace kvhbm

@@ -51,10 +51,17 @@ __device__ __forceinline__ unsigned long long gtime_plan() {
 }
 #endif
 
-constexpr int AP_THREADS = 320;
+// One block per SM, 20 warps.  A dependent FADD issues every 4 cycles only if its warp has the
+// SM sub-partition (warps w with the same w % 4) to itself: with four light warps sharing the
+// scheduler the chain ran at 10 cycles per add (measured, scripts/trace_apply_plan.py; alone:
+// 4.15, scripts/ub/faddchain.cu).  So while warp 0 walks the block's chains, the other warps of
+// its sub-partition (4, 8, 12, 16) sleep at a named barrier; the remaining 15 warps take light
+// ids from the start.
+constexpr int AP_THREADS = 640;
 constexpr int AP_NW = AP_THREADS / 32;
-constexpr int RING_ROWS = 64;     // occurrence rows per ring stage
-constexpr int RING_STAGES = 10;
+constexpr int AP_MATES = AP_NW / 4;   // warps of sub-partition 0, the consumer included
+constexpr int RING_ROWS = 128;    // occurrence rows per ring stage (one bulk copy, 16 KB)
+constexpr int RING_STAGES = 5;
 constexpr int RING_PITCH = 128;   // bytes per row part (32 columns)
 constexpr int RING_BYTES = RING_STAGES * RING_ROWS * RING_PITCH;  // 80 KB
 
@@ -66,10 +73,6 @@ struct Ring {
   unsigned long long* full;
   unsigned long long* empty;
   unsigned no;
-#ifdef KVHBM_TRACE
-  long long waited;   // cycles the consumer spent waiting for full stages
-  long long t_chain;  // cycles of the first chain this warp walked
-#endif
 };
 
 // Why the heavy rows are staged first (measured on B200, scripts/ub/rowgather*.cu): one SM
@@ -133,7 +136,7 @@ stage_heavy_kernel(const __grid_constant__ PlanView pl, const float* __restrict_
 // [e0, e0 + c) of pos — in list order from +0.  Warp 0 walks the chain out of the ring, one
 // column per lane, four units (16 rows) pulled into registers ahead of the adds so that the
 // chain itself is nothing but dependent FADDs; lane 0 of warp 1 keeps the ring full with one
-// bulk copy per stage (16 units, 8 KB) out of the staged part `part0` (unit 0 of the part).
+// bulk copy per stage (32 units, 16 KB) out of the staged part `part0` (unit 0 of the part).
 // The first and the last stage may hold rows of neighbouring ids: they are added under a
 // predicate, the stages in between unconditionally.  Returns the sum (warp 0).
 __device__ __forceinline__ float chain_item(Ring& rg, int wib, int lane, const float* __restrict__ part0,
@@ -146,76 +149,79 @@ __device__ __forceinline__ float chain_item(Ring& rg, int wib, int lane, const f
   rg.no += (unsigned)nst;
   float acc = 0.f;
   if (wib == 0) {
-#ifdef KVHBM_TRACE
-    const long long tc0 = clock64();
-#endif
-    float4 a[4], b[4];
-    const float4* st = nullptr;
-#define KV_LOAD(dst, c0) _Pragma("unroll") for (int j = 0; j < 4; ++j) dst[j] = st[((c0) * 4 + j) * 32]
-#define KV_ADD(v) if (dbg != 2) { _Pragma("unroll") for (int j = 0; j < 4; ++j) { acc += v[j].x; acc += v[j].y; acc += v[j].z; acc += v[j].w; } } else { acc += v[0].x + v[1].x + v[2].x + v[3].x; }
-    bool have_a = false;
-    for (int s = 0; s < nst; ++s) {
-      const unsigned no = no0 + (unsigned)s;
-      const unsigned e = no % RING_STAGES;
-      if (!have_a) {
-#ifdef KVHBM_TRACE
-        const long long w0 = clock64();
-#endif
-        mbar_wait(&rg.full[e], (no / RING_STAGES) & 1u);
-#ifdef KVHBM_TRACE
-        rg.waited += clock64() - w0;
-#endif
-        st = reinterpret_cast<const float4*>(rg.base + (size_t)e * RING_ROWS * RING_PITCH) + lane;
-      }
-      if (s == 0 || s == nst - 1) {
-        const int ub = u0 + s * SU;
-        const int nun = u1 - ub < SU ? u1 - ub : SU;
-        for (int j = 0; j < nun; ++j) {
-          const float4 v = st[j * 32];
-          const int row = (ub + j) * 4;
-          if (row >= e0 && row < e1) acc += v.x;
-          if (row + 1 >= e0 && row + 1 < e1) acc += v.y;
-          if (row + 2 >= e0 && row + 2 < e1) acc += v.z;
-          if (row + 3 >= e0 && row + 3 < e1) acc += v.w;
+    // running ring entry / parity of the stage being read (no divisions in the loop)
+    unsigned e = no0 % RING_STAGES, par = (no0 / RING_STAGES) & 1u;
+    auto stage_ptr = [&](unsigned ent) {
+      return reinterpret_cast<const float4*>(rg.base + (size_t)ent * RING_ROWS * RING_PITCH) + lane;
+    };
+    auto next_entry = [&]() { if (++e == RING_STAGES) { e = 0; par ^= 1u; } };
+    // a boundary stage: rows outside [e0, e1) belong to neighbouring ids.  Four units (16 rows)
+    // at a time, loads first; only a batch that straddles an end of the run pays for predicates
+    auto boundary = [&](int s) {
+      mbar_wait(&rg.full[e], par);
+      const float4* st = stage_ptr(e);
+      const int ub = u0 + s * SU;
+      const int nun = u1 - ub < SU ? u1 - ub : SU;
+      for (int j0 = 0; j0 < nun; j0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = j0 + j < nun ? st[(j0 + j) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row0 = (ub + j0) * 4;
+        if (row0 >= e0 && row0 + 16 <= e1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc += v[j].x; acc += v[j].y; acc += v[j].z; acc += v[j].w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = row0 + j * 4;
+            if (row >= e0 && row < e1) acc += v[j].x;
+            if (row + 1 >= e0 && row + 1 < e1) acc += v[j].y;
+            if (row + 2 >= e0 && row + 2 < e1) acc += v[j].z;
+            if (row + 3 >= e0 && row + 3 < e1) acc += v[j].w;
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rg.empty[e]);
-        have_a = false;
-      } else {
-        if (!have_a) KV_LOAD(a, 0);
-        KV_LOAD(b, 1);
-        KV_ADD(a);
-        KV_LOAD(a, 2);
-        KV_ADD(b);
-        KV_LOAD(b, 3);
-        KV_ADD(a);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty[e]);
+      next_entry();
+    };
+    boundary(0);
+    if (nst > 2) {
+      // interior stages: a tight loop of nothing but 128-bit loads issued a chunk (16 rows)
+      // ahead, dependent adds, and one barrier round per stage
+      static_assert(RING_ROWS == 128, "eight chunks per stage");
+      float4 a[4], b[4];
+#define KV_LOAD(dst, c0) _Pragma("unroll") for (int j = 0; j < 4; ++j) dst[j] = st[((c0) * 4 + j) * 32]
+#define KV_ADD(v) _Pragma("unroll") for (int j = 0; j < 4; ++j) { acc += v[j].x; acc += v[j].y; acc += v[j].z; acc += v[j].w; }
+      mbar_wait(&rg.full[e], par);
+      const float4* st = stage_ptr(e);
+      KV_LOAD(a, 0);
+#pragma unroll 1
+      for (int s = 1; s < nst - 1; ++s) {
+        KV_LOAD(b, 1); KV_ADD(a);
+        KV_LOAD(a, 2); KV_ADD(b);
+        KV_LOAD(b, 3); KV_ADD(a);
+        KV_LOAD(a, 4); KV_ADD(b);
+        KV_LOAD(b, 5); KV_ADD(a);
+        KV_LOAD(a, 6); KV_ADD(b);
+        KV_LOAD(b, 7); KV_ADD(a);
         __syncwarp();
         if (lane == 0) mbar_arrive(&rg.empty[e]);   // the stage is in registers: hand it back
-        if (s + 1 < nst - 1) {                      // the next stage is an interior one too
-          const unsigned e1n = (no + 1u) % RING_STAGES, par = ((no + 1u) / RING_STAGES) & 1u;
-#ifdef KVHBM_TRACE
-          const long long w0 = clock64();
-#endif
-          unsigned ok = mbar_test(&rg.full[e1n], par);
+        next_entry();
+        if (s + 1 < nst - 1) {
+          unsigned ok = mbar_test(&rg.full[e], par);
           KV_ADD(b);
-          while (!ok) ok = mbar_test(&rg.full[e1n], par);
-#ifdef KVHBM_TRACE
-          rg.waited += clock64() - w0;
-#endif
-          st = reinterpret_cast<const float4*>(rg.base + (size_t)e1n * RING_ROWS * RING_PITCH) + lane;
+          while (!ok) ok = mbar_test(&rg.full[e], par);
+          st = stage_ptr(e);
           KV_LOAD(a, 0);
-          have_a = true;
         } else {
           KV_ADD(b);
-          have_a = false;
         }
       }
-    }
 #undef KV_LOAD
 #undef KV_ADD
-#ifdef KVHBM_TRACE
-    if (no0 == 0) rg.t_chain = clock64() - tc0;
-#endif
+    }
+    if (nst > 1) boundary(nst - 1);
   } else if (wib == 1 && lane == 0) {
     for (int s = 0; s < nst; ++s) {
       const unsigned no = no0 + (unsigned)s;
@@ -229,6 +235,30 @@ __device__ __forceinline__ float chain_item(Ring& rg, int wib, int lane, const f
     }
   }
   return acc;
+}
+
+// Heavy items: a block's first item is static (item blockIdx.x), the following ones come from
+// a counter, so a block that is still walking a long chain takes nothing more.  The consumer
+// (warp 0) draws the item and posts it for the block's producer thread.
+struct ItemMail {
+  volatile long long item;
+  volatile unsigned seq;
+};
+__device__ __forceinline__ long long next_item_consumer(ItemMail* mail, unsigned* work, unsigned& seq, int lane) {
+  long long nxt = 0;
+  if (lane == 0) {
+    nxt = (long long)gridDim.x + atomicAdd(&work[2], 1u);
+    mail->item = nxt;
+    __threadfence_block();
+    mail->seq = ++seq;
+  }
+  return __shfl_sync(0xffffffffu, nxt, 0);
+}
+__device__ __forceinline__ long long next_item_producer(ItemMail* mail, unsigned& seq) {
+  ++seq;
+  while (mail->seq < seq) __nanosleep(64);
+  __threadfence_block();
+  return mail->item;
 }
 
 // Light groups are handed out through a counter in the plan (blocks that spend their time on
@@ -245,37 +275,24 @@ __device__ __forceinline__ void work_epilogue(unsigned* work) {
     if (atomicAdd(&work[1], 1u) == gridDim.x - 1) {
       work[0] = 0u;
       work[1] = 0u;
+      work[2] = 0u;
+      work[3] = 0u;
     }
   }
 }
 
-// The apply of one heavy id by the warp that completed its sum.  Not inlined: it runs once
-// per heavy id, and keeping a second copy of the group routine out of the kernel body leaves
-// the registers to the light path.
 template <int VEC, int CPL, int KIND>
-__device__ __noinline__ void apply_heavy_id(ApplySmem<AP_NW, VEC, CPL>* sm, int wib,
-                                            const TableView* var, const TableView* sa,
-                                            const TableView* sb, const PlanView* pl, int h, int r,
-                                            const ApplyParams* p, uint32_t today, int tpr) {
-  GradSrc gs;
-  gs.grad = pl->heavy_sum + (size_t)h * pl->sum_dim; gs.row0 = r; gs.counts = nullptr;
-  gs.seg_off = nullptr; gs.pos = nullptr; gs.heavy_t = 0; gs.hint = pl->hint; gs.cg = true;
-  apply_group<AP_NW, VEC, CPL, KIND, 1, 1>(*sm, wib, *var, *sa, *sb, pl->uniq, gs, r, (long long)r + 1,
-                                           *p, today, tpr, 32 / tpr, true);
-}
-
-template <int VEC, int CPL, int KIND>
-__global__ void __launch_bounds__(AP_THREADS, 2)
+__global__ void __launch_bounds__(AP_THREADS, 1)
 apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__ TableView sa,
                   const __grid_constant__ TableView sb, const __grid_constant__ PlanView pl,
                   const float* __restrict__ grad, const __grid_constant__ ApplyParams p_in,
-                  const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv,
-                  int excl) {
+                  const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv) {
   ApplyParams p = p_in;
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p_in.update_slots);
-  __shared__ ApplySmem<AP_NW, VEC, CPL> sm;
-  extern __shared__ __align__(128) unsigned char ring[];
+  extern __shared__ __align__(128) unsigned char ring[];   // ring, then the light path's staging
+  ApplySmem<AP_NW, VEC, CPL>& sm = *reinterpret_cast<ApplySmem<AP_NW, VEC, CPL>*>(ring + RING_BYTES);
   __shared__ unsigned long long full_bar[RING_STAGES], empty_bar[RING_STAGES];
+  __shared__ ItemMail mail;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dim = var.dim;
   const long long U = *pl.num;
@@ -283,6 +300,7 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mail.seq = 0u;
     fence_async_smem();
   }
   __syncthreads();
@@ -300,35 +318,49 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
   // ---- heavy ids first: their chains are the longest thing in the launch ----
   Ring rg;
   rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.no = 0;
-#ifdef KVHBM_TRACE
-  rg.waited = 0; rg.t_chain = 0;
-#endif
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-    const int r = pl.heavy[h];
-    const int c = pl.counts[r], off = pl.seg_off[r];
-    const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
-    const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128, off, c, excl);
-    if (wib == 0) {
-      if (lane < width) __stcg(pl.heavy_sum + (size_t)h * pl.sum_dim + part * 32 + lane, acc);
-      __threadfence();
-      unsigned last = 0;
-      if (lane == 0) last = atomicAdd(&pl.heavy_done[h], 1u) == (unsigned)(parts - 1);
-      last = __shfl_sync(APPLY_FULL, last, 0);
-      if (last) {
-        // every part of this id has been parked: apply it (the counter goes back to zero for
-        // the next launch)
-        if (lane == 0) pl.heavy_done[h] = 0u;
+  if (wib < 2 && (wib == 0 || lane == 0)) {
+    unsigned seq = 0;
+    long long it = blockIdx.x;
+    while (it < items) {
+      const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
+      const int r = pl.heavy[h];
+      const int c = pl.counts[r], off = pl.seg_off[r];
+      const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
+      const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128, off, c);
+      if (wib == 0) {
+        if (lane < width) __stcg(pl.heavy_sum + (size_t)h * pl.sum_dim + part * 32 + lane, acc);
         __threadfence();
-        apply_heavy_id<VEC, CPL, KIND>(&sm, wib, &var, &sa, &sb, &pl, h, r, &p, today, tpr);
+        if (lane == 0) atomicAdd(&pl.heavy_done[h], 1u);   // the id is applied by whoever took it below
+        it = next_item_consumer(&mail, pl.work, seq, lane);
+      } else {
+        it = next_item_producer(&mail, seq);
       }
     }
   }
+  __syncwarp();
 
-  if (excl && blockIdx.x < items) __syncthreads();   // (experiment) light work waits for the chain
+  // the consumer's sub-partition mates start their light work when the block's chains are done
+  if ((wib & 3) == 0 && blockIdx.x < items)
+    asm volatile("bar.sync 1, %0;" ::"n"(AP_MATES * 32) : "memory");
 #ifdef KVHBM_TRACE
   if (trace) t_heavy = gtime_plan();
 #endif
+  // ---- the applies of the heavy ids: taken first, so that an id's probes and row loads are
+  // long done when its chain delivers the sum (apply_group waits right before it needs it) ----
+  {
+    GradSrc gs;
+    gs.grad = pl.heavy_sum; gs.row0 = 0; gs.counts = nullptr; gs.seg_off = nullptr; gs.pos = nullptr;
+    gs.heavy_t = 0; gs.hint = pl.hint; gs.cg = true;
+    gs.remap = pl.heavy; gs.ready = pl.heavy_done; gs.ready_n = (unsigned)parts; gs.gstride = pl.sum_dim;
+    const int kpi = 32 / tpr;
+    for (;;) {
+      unsigned b = 0;
+      if (lane == 0) b = atomicAdd(&pl.work[3], (unsigned)kpi);
+      const long long base = (long long)__shfl_sync(0xffffffffu, b, 0);
+      if (base >= H) break;
+      apply_group<AP_NW, VEC, CPL, KIND, 1, 1>(sm, wib, var, sa, sb, ids, gs, base, H, p, today, tpr, kpi, true);
+    }
+  }
   // ---- light ids ----
   {
     GradSrc gs;
@@ -348,7 +380,7 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
   if (trace && lane == 0) {
     unsigned long long* r = trace + ((size_t)blockIdx.x * AP_NW + wib) * 4;
     r[0] = t_start; r[1] = t_heavy; r[2] = gtime_plan();
-    r[3] = wib == 0 ? ((unsigned long long)rg.waited & 0xffffffffull) | ((unsigned long long)rg.t_chain << 32) : n_groups;
+    r[3] = n_groups;
   }
 #endif
   work_epilogue(pl.work);
@@ -374,15 +406,17 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
 // fused kernel: blocks walk the heavy ids' chains through the ring first, then every warp
 // takes light segments, a tile per segment.
 template <int VEC>
-__global__ void __launch_bounds__(AP_THREADS, 2)
+__global__ void __launch_bounds__(AP_THREADS, 1)
 segsum_plan_kernel(const __grid_constant__ PlanView pl, const float* __restrict__ data, int dim,
                    float* __restrict__ out, int tpr) {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ unsigned long long full_bar[RING_STAGES], empty_bar[RING_STAGES];
+  __shared__ ItemMail mail;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long U = *pl.num;
   if (threadIdx.x == 0) {
     for (int s = 0; s < RING_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mail.seq = 0u;
     fence_async_smem();
   }
   __syncthreads();
@@ -392,14 +426,26 @@ segsum_plan_kernel(const __grid_constant__ PlanView pl, const float* __restrict_
   const long long items = (long long)H * parts;
   Ring rg;
   rg.base = ring; rg.full = full_bar; rg.empty = empty_bar; rg.no = 0;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
-    const int r = pl.heavy[h];
-    const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
-    const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128,
-                                 pl.seg_off[r], pl.counts[r]);
-    if (wib == 0 && lane < width) out[(long long)r * dim + part * 32 + lane] = acc;
+  if (wib < 2 && (wib == 0 || lane == 0)) {
+    unsigned seq = 0;
+    long long it = blockIdx.x;
+    while (it < items) {
+      const int h = (int)(it / parts), part = (int)(it - (long long)h * parts);
+      const int r = pl.heavy[h];
+      const int width = dim - part * 32 < 32 ? dim - part * 32 : 32;
+      const float acc = chain_item(rg, wib, lane, pl.staged + (size_t)part * pl.staged_units * 128,
+                                   pl.seg_off[r], pl.counts[r]);
+      if (wib == 0) {
+        if (lane < width) out[(long long)r * dim + part * 32 + lane] = acc;
+        it = next_item_consumer(&mail, pl.work, seq, lane);
+      } else {
+        it = next_item_producer(&mail, seq);
+      }
+    }
   }
+  __syncwarp();
+  if ((wib & 3) == 0 && blockIdx.x < items)
+    asm volatile("bar.sync 1, %0;" ::"n"(AP_MATES * 32) : "memory");
   // a tile of `tpr` lanes per light segment, elements strided by the tile (any dim), the rows
   // of a segment fetched four at a time
   const int tl = lane & (tpr - 1);
@@ -492,8 +538,7 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
                       const ApplyParams& p, const float* d_hp, uint16_t today, cudaStream_t st,
                       int tpr, float* d_adv) {
   static const int kpw_env = getenv("KVHBM_APPLYP_KPW") ? atoi(getenv("KVHBM_APPLYP_KPW")) : 0;
-  static const int excl_env = getenv("KVHBM_APPLYP_EXCL") ? atoi(getenv("KVHBM_APPLYP_EXCL")) : 0;
-  static const int bps_env = getenv("KVHBM_APPLYP_BPS") ? atoi(getenv("KVHBM_APPLYP_BPS")) : 2;
+  constexpr int bps_env = 1;
   const int sms = sm_count(var->device);
   const int kpi = 32 / tpr;
   // light warps of a full grid; a Zipf batch has ~n/3 distinct ids
@@ -506,15 +551,16 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
   if (blocks > (long long)sms * bps_env) blocks = (long long)sms * bps_env;
   if (blocks < 1) blocks = 1;
   auto kern = apply_plan_kernel<VEC, CPL, KIND>;
+  const size_t smem = RING_BYTES + sizeof(ApplySmem<AP_NW, VEC, CPL>);
   static bool attr = false;  // per instantiation
   if (!attr) {
-    KV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_BYTES));
+    KV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   TableView vb = sb ? sb->view() : sa->view();
   KV_TRY(launch_stage_heavy(pv, grad, var->dim, var->device, st));
-  kern<<<(unsigned)blocks, AP_THREADS, RING_BYTES, st>>>(var->view(), sa->view(), vb, pv, grad, p, d_hp,
-                                                        today, tpr, kpw, d_adv, excl_env);
+  kern<<<(unsigned)blocks, AP_THREADS, smem, st>>>(var->view(), sa->view(), vb, pv, grad, p, d_hp,
+                                                  today, tpr, kpw, d_adv);
   KV_LAUNCHED();
   return 0;
 }
@@ -573,7 +619,7 @@ int do_segment_sum_plan(Plan* plan, const float* data, int dim, float* out, cuda
   const int sms = sm_count(dev);
   const long long tiles_per_block = (long long)AP_NW * (32 / g.tpr);
   long long blocks = (pv.n + tiles_per_block - 1) / tiles_per_block;
-  if (blocks > 2LL * sms) blocks = 2LL * sms;
+  if (blocks > (long long)sms) blocks = sms;
   if (blocks < 1) blocks = 1;
   KV_TRY(launch_stage_heavy(pv, data, dim, dev, st));
   if (g.vec == 4)

@@ -205,8 +205,9 @@ class PaddedShardedStep:
 
   def run(self, ids, grad, out=None):
     """All NCCL calls stay on the calling stream in a fixed order; work that only depends on
-    the ids (local gradient sum, the owner-side dedup) runs on a side stream underneath the
-    exchanges and is joined where its result is needed."""
+    the ids (the owner-side dedup) runs on a side stream underneath the exchanges and is
+    joined where its result is needed.  The gradient is a function of the gathered rows, so
+    nothing of the backward half starts before the rows have been expanded."""
     B, G, C, D = self.batch, self.world, self.cap, self.dim
     t = torch
     main = t.cuda.current_stream(self.dev)
@@ -217,10 +218,6 @@ class PaddedShardedStep:
       ops.route_id_pairs(self.uniq, self.cnt, G, C, self.mode, self.num, self.route)
     else:
       ops.route_ids(self.uniq, self.cnt, G, C, self.mode, num_ids=self.num, out=self.route)
-    side.wait_stream(main)
-    with t.cuda.stream(side):      # backward, local half: sum duplicate gradients, lay them out
-      ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
-      ops.scatter_rows_n(self.gsum, self.route["perm"], B, self.num, self.g_send)
     if self.pairs:
       self._a2a(self.recv_pairs, self.route["send_pairs"])   # ids + occurrence counts together
       ops.unzip_pairs(self.recv_pairs, self.recv_ids, self.recv_occ)
@@ -238,7 +235,10 @@ class PaddedShardedStep:
     self._a2a(self.rows_recv, self.rows_owner)
     out = self.out if out is None else out
     ops.expand_rows(self.rows_recv, self.route["perm"], self.idx, B, out)
-    # ---- backward: route gradients, owner merge, fused apply ----
+    # ---- [the model runs here: `grad` is a function of `out`] ----
+    # ---- backward: sum duplicate gradients, route them, owner merge, fused apply ----
+    ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
+    ops.scatter_rows_n(self.gsum, self.route["perm"], B, self.num, self.g_send)
     main.wait_stream(side)
     self._a2a(self.g_recv, self.g_send)
     ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum,
@@ -281,23 +281,25 @@ class PeerShardedStep(PaddedShardedStep):
   """PaddedShardedStep without NCCL in the data path: every exchange is the stores of the
   kernel that produces the data, written straight into the destination GPU's buffer over
   NVLink (kv_unique_route_peer, kv_gather_or_insert_peer, kv_scatter_rows_n_peer), and the only
-  cross-GPU synchronisation is two kv_peer_barrier kernels per step:
+  cross-GPU synchronisation is three kv_peer_barrier kernels per step, one per exchange of the
+  reference's data flow (ids -> rows -> [model] -> gradients):
 
-    unique+route ==ids==> | barrier A | owner lookup ==rows==>      | barrier B | expand rows
-           -> local grad sums         | grad sums    ==grads==>     |           | owner sum, apply
-                                      | owner-side dedup            |
+    unique+route ==ids==> |A| owner lookup ==rows==> |B| expand rows -> [model] ->
+                          | | owner-side dedup       | | local grad sums ==grads==> |C| owner sum, apply
 
-  (ids and gradients are both inputs of the step, as in the single-GPU step, so the gradient
-  exchange shares barrier B with the rows.)  Buffer reuse across steps needs no extra barrier:
-  a rank stores into a peer's inbox only after barrier B of an earlier step, which the peer
-  reaches after its last read of that inbox; into a peer's row / gradient buffers only after
-  barrier A, which the peer reaches after the previous step's expand / owner sum.
+  The gradient of a batch is a function of its gathered rows, so the gradient sums leave a
+  requester only after barrier B has delivered the rows and they have been expanded.  Buffer
+  reuse across steps needs no extra barrier: a rank stores into a peer's inbox only after
+  barrier B of an earlier step, which the peer reaches after its last read of that inbox; into
+  a peer's row buffer only after barrier A, which the peer reaches after the expand of the
+  step that used the buffer before; into a peer's gradient buffer only after barrier B, which
+  the peer reaches after the owner sum that read the buffer before.
 
   `run` is one step, strictly after the previous one.  `run_rotation` issues a list of steps
-  with only their true dependencies (the requester-side dedup, routing and gradient sum of
-  step t+1, barrier A(t+1) and the owner-side dedup(t+1) run under the owner phase of step t):
-  every exchange buffer and both dedup buffer sets exist twice and alternate, barriers A and B
-  use separate flag channels, everything else is ordered by events and the barriers."""
+  and lets only what depends on the ids alone run ahead: the requester-side dedup + routing of
+  step t+1 (the id exchange), barrier A(t+1) and the owner-side dedup(t+1) run under step t.
+  Every exchange buffer and both dedup buffer sets exist twice and alternate, barriers A, B
+  and C use separate flag channels, everything else is ordered by events and the barriers."""
 
   def __init__(self, *a, **kw):
     super().__init__(*a, **kw)
@@ -310,7 +312,7 @@ class PeerShardedStep(PaddedShardedStep):
     for name, nbytes in (("flags", 4 * G), ("ids", G * C * 8), ("occ", G * C * 4),
                          ("rows", G * C * D * 4), ("grads", G * C * D * 4)):
       off[name] = []
-      for _ in range(2):
+      for _ in range(3 if name == "flags" else 2):
         off[name].append(cur)
         cur += al(nbytes)
     self.peer = PeerMemory(cur, self.dev, self.group)
@@ -325,13 +327,13 @@ class PeerShardedStep(PaddedShardedStep):
     self.seg_occ = [pm.table(o + r * C * 4) for o in off["occ"]]
     self.seg_rows = [pm.table(o + r * C * D * 4) for o in off["rows"]]
     self.seg_grads = [pm.table(o + r * C * D * 4) for o in off["grads"]]
-    self.bstate = [t.zeros(2, dtype=t.int32, device=self.dev) for _ in range(2)]
+    self.bstate = [t.zeros(2, dtype=t.int32, device=self.dev) for _ in range(3)]
     self.barrier_ms = int(os.environ.get("KVHBM_PEER_TIMEOUT_MS", "2000"))
     self.side2 = t.cuda.Stream(device=self.dev)
     self.side3 = t.cuda.Stream(device=self.dev)
     self.side4 = t.cuda.Stream(device=self.dev)
     self.side5 = t.cuda.Stream(device=self.dev)
-    self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)
+    self.wire_bytes = (G - 1) * C * (12 + 2 * 4 * D)      # capacity (padded) bytes per step
     # requester-side and owner-side dedup buffers, two sets (set 0 = the ones `run` uses)
     i64 = dict(dtype=t.int64, device=self.dev)
     i32 = dict(dtype=t.int32, device=self.dev)
@@ -360,7 +362,7 @@ class PeerShardedStep(PaddedShardedStep):
                      self.rank, self.world, self.barrier_ms)
 
   def barrier_timeouts(self):
-    return int(self.bstate[0][1].item()) + int(self.bstate[1][1].item())
+    return sum(int(b[1].item()) for b in self.bstate)
 
   def _owner_update(self, p=0):
     O = self.osets[p]
@@ -381,9 +383,6 @@ class PeerShardedStep(PaddedShardedStep):
                             self.seg_ids[0], self.seg_occ[0], self.route)
     else:
       ops.unique_into(ids, self.uniq, self.idx, self.cnt, self.num)
-    s2.wait_stream(main)
-    with t.cuda.stream(s2):        # sum duplicate gradients locally
-      ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
     if not self.fused_route:       # route = the id exchange: ids / counts land in the owners' inboxes
       ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
       ops.route_ids_peer(self.uniq, self.cnt, G, C, self.mode, self.num, self.seg_ids[0],
@@ -395,40 +394,35 @@ class PeerShardedStep(PaddedShardedStep):
       s1.wait_event(ev_a)
       ops.unique_into(self.ids_in[0], self.o_uniq, self.o_idx, None, self.o_num,
                       ws=self.ws_owner)
-    with t.cuda.stream(s2):        # gradient exchange: sums go to the owners' buffers
-      s2.wait_event(ev_a)
-      ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads[0], C)
       ops.zero_rows(self.o_gsum)
     # owner lookup = the row exchange: rows land in the requesters' buffers
     ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[0], self.occ_in[0],
                                           self.seg_rows[0], C)
-    main.wait_stream(s1)
-    main.wait_stream(s2)
-    self._barrier()                # B: my rows and every peer's gradient sums have arrived
-    ev_b = t.cuda.Event()
-    ev_b.record(main)
-    # the longer branch is issued first: a captured graph keeps the first dependent of a node
-    # on the node's own stream and pays ~5 us of cross-stream latency for the others
+    main.wait_stream(s1)           # arriving at B also says: I am done reading my inbox
+    self._barrier()                # B: my rows have arrived
+    if self.fused_route:           # every owner has read its inbox: pad it for the next step
+      ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
+    ops.expand_rows(self.rows_in[0], self.route["perm"], self.idx, B, out)
+    # ---- [the model runs here: `grad` is a function of `out`] ----
+    ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
+    # gradient exchange: the sums go to the owners' buffers
+    ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads[0], C)
+    self._barrier()                # C: every peer's gradient sums have arrived
     self._owner_update()
-    with t.cuda.stream(s1):
-      s1.wait_event(ev_b)
-      if self.fused_route:         # every owner has read its inbox: pad it for the next step
-        ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
-      ops.expand_rows(self.rows_in[0], self.route["perm"], self.idx, B, out)
-    main.wait_stream(s1)
     return out
 
   def run_rotation(self, ids_list, grad_list, out=None):
-    """len(ids_list) (even) consecutive steps with only their true dependencies.
+    """len(ids_list) (even) consecutive steps; only what depends on the ids alone runs ahead.
 
-    The one chain that must run step after step is  lookup(t) -> barrier B(t) -> owner sum(t)
-    -> apply(t) -> lookup(t+1)  (a lookup reads what the previous apply wrote); it is issued on
-    the calling stream.  Everything else is fed to it from the side:
+    The chain that must run step after step is  lookup(t) -> barrier B(t) -> expand(t) ->
+    [model] -> local gradient sum(t) -> gradient exchange(t) -> barrier C(t) -> owner sum(t) ->
+    apply(t) -> lookup(t+1).  Fed to it from the side:
       s_r  requester: dedup+route(t) [= id exchange], step after step;
-      s_g  local gradient sum(t) and - once barrier B(t-1) has passed - the gradient exchange(t);
       s_o  barrier A(t) (channel 0: every peer's ids(t) are in my inbox) and the owner-side
-           dedup(t), which therefore runs under the owner phase of step t-1;
-      s_e  after barrier B(t): pad the inbox for step t+2, expand the rows of step t.
+           dedup(t), which therefore run under step t-1;
+      s_z  the zero-fill of the owner sums' destination;
+      s_e  after barrier B(t): pad the inbox for step t+2, expand the rows of step t, then the
+           local gradient sum and the gradient exchange of step t (they follow the expand).
     Step t uses buffer set t % 2 of everything exchanged.  Who may overwrite what, and why it
     is safe, is argued hazard by hazard in DESIGN.md (section 6)."""
     assert len(ids_list) % 2 == 0 and self.fused_route
@@ -436,32 +430,21 @@ class PeerShardedStep(PaddedShardedStep):
     t = torch
     out = self.out if out is None else out
     main = t.cuda.current_stream(self.dev)
-    s_r, s_o, s_e, s_z, s_g = self.side, self.side2, self.side3, self.side4, self.side5
-    for s in (s_r, s_o, s_e, s_z, s_g):
+    s_r, s_o, s_e, s_z = self.side, self.side2, self.side3, self.side4
+    for s in (s_r, s_o, s_e, s_z):
       s.wait_stream(main)
-    ev_e = [None, None]       # expand (+ inbox padding) of the last step on buffer set p
-    ev_r3 = [None, None]      # gradient exchange of the last step on buffer set p
+    ev_g = [None, None]       # expand + gradient exchange of the last step on buffer set p
     ev_apply = [None, None]   # apply of the last step on buffer set p
-    ev_b_prev = None          # barrier B of the previous step
     for step, (ids, grad) in enumerate(zip(ids_list, grad_list)):
       p = step & 1
       S, O = self.sets[p], self.osets[p]
       with t.cuda.stream(s_r):     # requester: nothing here depends on the table
-        if ev_e[p] is not None:
-          s_r.wait_event(ev_e[p])  # set p's perm / idx were read, and inbox p padded, by then
-          s_r.wait_event(ev_r3[p])
+        if ev_g[p] is not None:
+          s_r.wait_event(ev_g[p])  # set p's perm / idx / sums were read, and inbox p padded, by then
         ops.unique_route_peer(ids, S["uniq"], S["idx"], S["cnt"], S["num"], G, C, self.mode,
                               self.seg_ids[p], self.seg_occ[p], S["route"])
         ev_r1 = t.cuda.Event()
         ev_r1.record(s_r)
-      with t.cuda.stream(s_g):     # gradients: local sums, then the exchange (own chain, so the
-        s_g.wait_event(ev_r1)      # next step's dedup does not queue behind barrier B(t-1))
-        ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"])
-        if ev_b_prev is not None:
-          s_g.wait_event(ev_b_prev)  # the owners have passed B(t-1): done with grads_in[p] of t-2
-        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads[p], C)
-        ev_r3[p] = t.cuda.Event()
-        ev_r3[p].record(s_g)
       with t.cuda.stream(s_o):
         s_o.wait_event(ev_r1)      # my ids are stored before I say so
         self._barrier(0)           # A(t)
@@ -483,24 +466,25 @@ class PeerShardedStep(PaddedShardedStep):
       ops.kv_variable_gather_or_insert_peer(self.var, self.ids_in[p], self.occ_in[p],
                                             self.seg_rows[p], C)
       main.wait_event(ev_ub)       # arriving at B also says: I am done reading inbox p
-      main.wait_event(ev_r3[p])    # ... and my gradient sums are stored
-      if ev_e[1 - p] is not None:
-        main.wait_event(ev_e[1 - p])   # ... and I have read rows_in[1-p] (lookup t+1 rewrites it)
-      main.wait_event(ev_z)
-      self._barrier(1)             # B(t)
+      self._barrier(1)             # B(t): my rows have arrived
       ev_b = t.cuda.Event()
       ev_b.record(main)
-      ev_b_prev = ev_b
-      self._owner_update(p)
-      ev_apply[p] = t.cuda.Event()
-      ev_apply[p].record(main)
       with t.cuda.stream(s_e):
         s_e.wait_event(ev_b)
         ops.route_fill_peer(G, C, self.seg_ids[p], self.seg_occ[p], S["route"]["counts"])
         ops.expand_rows(self.rows_in[p], S["route"]["perm"], S["idx"], B, out)
-        ev_e[p] = t.cuda.Event()
-        ev_e[p].record(s_e)
-    for s in (s_r, s_o, s_e, s_z, s_g):
+        # [the model runs here: `grad` is a function of `out`]
+        ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"])
+        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads[p], C)
+        ev_g[p] = t.cuda.Event()
+        ev_g[p].record(s_e)
+      main.wait_event(ev_g[p])     # my gradient sums are stored before I say so
+      main.wait_event(ev_z)
+      self._barrier(2)             # C(t): every peer's gradient sums have arrived
+      self._owner_update(p)
+      ev_apply[p] = t.cuda.Event()
+      ev_apply[p].record(main)
+    for s in (s_r, s_o, s_e, s_z):
       main.wait_stream(s)
     return out
 
@@ -520,195 +504,3 @@ def make_padded_step(*a, **kw):
       sys.stderr.write("[kvhbm] peer-memory exchange unavailable (%s: %s); using NCCL\n"
                        % (type(e).__name__, e))
   return PaddedShardedStep(*a, **kw)
-
-
-# ---------------------------------------------------------------------------
-# bench driver (bench.py --gpus N)
-# ---------------------------------------------------------------------------
-class ShardedStepper:
-  """Weak-scaling microbench: `keys` keys per GPU, every rank brings its own batch."""
-
-  STAGES = ["route+lookup", "grads+apply"]
-
-  def __init__(self, keys_per_gpu, dim, batch, hp, dev, rank, world):
-    import bench
-    self.torch = torch
-    self.keys, self.dim, self.batch, self.dev = keys_per_gpu, dim, batch, dev
-    self.rank, self.world, self.hp = rank, world, hp
-    cap = int(keys_per_gpu * 1.15) + batch
-    self.tbl = ShardedKvVariable(dim, world, rank, dev, slot_dims=(3 * dim,),
-                                 capacity_hint=cap, seed=1)
-    ops.init_kv_variable_v2(self.tbl.var, torch.from_numpy(bench.init_table(dim)).to(dev))
-    ops.init_kv_variable_v2(self.tbl.slots[0], torch.zeros(bench.INIT_ROWS, 3 * dim, device=dev))
-    self.hpt = torch.tensor([hp["lr"], hp["beta1"], hp["beta2"], hp["beta1"], hp["beta2"],
-                             hp["epsilon"], hp["l1"], hp["l2"], hp["l21"]], dtype=torch.float32,
-                            device=dev)
-    self.betas = torch.tensor([hp["beta1"], hp["beta2"]], dtype=torch.float32, device=dev)
-    self.launches_per_step = 0
-    self.steps_done = 0
-
-  def populate(self):
-    """Insert the keys this rank owns out of the global id range [0, keys * world)."""
-    t = self.torch
-    total = self.keys * self.world
-    chunk = 1 << 20
-    for s in range(0, total, chunk):
-      ids = t.arange(s, min(total, s + chunk), dtype=t.int64, device=self.dev)
-      sorted_ids, _, counts = ops.partition_ids(ids, self.world, "hash")
-      c = counts.cpu().tolist()
-      lo = sum(c[:self.rank])
-      mine = sorted_ids[lo:lo + c[self.rank]]
-      if mine.numel():
-        ops.kv_variable_gather_or_insert_v2(self.tbl.var, mine)
-        ops.kv_variable_gather_or_insert_v2(self.tbl.slots[0], mine)
-    t.cuda.synchronize()
-
-  def step_exact(self, ids, grad):
-    """The variable-size path (host reads the per-shard counts): reference behaviour for the
-    padded path and its fallback on overflow."""
-    rows = self.tbl.lookup(ids)
-    owner_ids, owner_grads = self.tbl.owner_gradients(grad)
-    if owner_ids.numel():
-      ops.kv_variable_group_sparse_apply_adam_v4_dev(self.tbl.var, self.tbl.slots[0], owner_grads,
-                                                     owner_ids, self.hpt)
-    self.hpt[1:3].mul_(self.betas)
-    return rows
-
-  def step_eager(self, ids, grad):
-    self.steps_done += 1
-    return self.padded.run(ids, grad)
-
-  def prepare(self, ids_d, grads_d):
-    from . import _lib
-    t = self.torch
-    self.ids_d, self.grads_d = ids_d, grads_d
-    self.padded = make_padded_step(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
-                                   self.world, self.rank, self.dev, self.hpt, self.betas)
-    l0 = _lib.launch_count()
-    for i in range(2):
-      self.step_eager(ids_d[i], grads_d[i])
-    self.launches_per_step = (_lib.launch_count() - l0) // 2
-    t.cuda.synchronize()
-    if self.padded.overflowed():
-      raise RuntimeError("padded shard exchange overflowed: raise cap")
-    ops.kv_variable_reserve(self.tbl.var, 2 * self.padded.cap * self.world)
-    ops.kv_variable_reserve(self.tbl.slots[0], 2 * self.padded.cap * self.world)
-    self.graphs = [self._capture(lambda i=i: self.padded.run(ids_d[i], grads_d[i]))
-                   for i in range(len(ids_d))]
-    if self.graphs and self.graphs[0] is None:
-      self.graphs = []
-    # the pipelined schedule: one graph per rotation of the batches (PeerShardedStep only)
-    self.rotation = None
-    if (self.graphs and hasattr(self.padded, "run_rotation") and self.padded.fused_route
-        and len(ids_d) % 2 == 0 and os.environ.get("KVHBM_BENCH_PIPELINE", "1") != "0"):
-      self.padded.run_rotation(ids_d, grads_d)        # once eagerly: errors surface here
-      t.cuda.synchronize()
-      self.rotation = self._capture(lambda: self.padded.run_rotation(ids_d, grads_d))
-    t.cuda.synchronize()
-
-  def run_steps(self, K):
-    """K consecutive steps: whole rotations as one graph each, the rest step by step."""
-    n, i = len(self.ids_d), 0
-    if self.rotation is not None:
-      while K - i >= n:
-        self.rotation.replay()
-        i += n
-      self.steps_done += i
-    while i < K:
-      self.step(i)
-      i += 1
-
-  def step(self, i):
-    k = i % len(self.ids_d)
-    self.steps_done += 1
-    if self.graphs:
-      self.graphs[k].replay()
-      return self.padded.out
-    return self.padded.run(self.ids_d[k], self.grads_d[k])
-
-  def release(self):
-    self.graphs = []
-    self.e2e = []
-    self.rotation = None
-
-  def stage_times(self, steps):
-    t = self.torch
-    a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-    t.cuda.synchronize()
-    a.record()
-    for i in range(steps):
-      self.step(i)
-    b.record()
-    t.cuda.synchronize()
-    return {"sharded step": a.elapsed_time(b) / steps}
-
-  def _capture(self, fn):
-    t = self.torch
-    if os.environ.get("KVHBM_SHARDED_GRAPH", "1") == "0":
-      return None
-    side = t.cuda.Stream(device=self.dev)
-    side.wait_stream(t.cuda.current_stream(self.dev))
-    with t.cuda.stream(side):
-      g = t.cuda.CUDAGraph()
-      with t.cuda.graph(g, stream=side):
-        fn()
-    t.cuda.current_stream(self.dev).wait_stream(side)
-    return g
-
-  def prepare_host(self, ids_h, grads_h, rows_h):
-    """End to end: every step copies its ids + gradients from pinned host memory and its rows
-    back.  Two input / output slots and two copy streams, so the H2D of step i+1 and the D2H
-    of step i-1 run under the kernels and exchanges of step i; every copy still happens once
-    per step inside the timed region."""
-    t = self.torch
-    self.ids_h, self.grads_h, self.rows_h = ids_h, grads_h, rows_h
-    self.s_h2d, self.s_d2h = t.cuda.Stream(device=self.dev), t.cuda.Stream(device=self.dev)
-    self.h_ids = [t.empty(self.batch, dtype=t.int64, device=self.dev) for _ in range(2)]
-    self.h_grad = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
-                   for _ in range(2)]
-    self.h_out = [t.empty((self.batch, self.dim), dtype=t.float32, device=self.dev)
-                  for _ in range(2)]
-    self.rows_host = [rows_h, t.empty_like(rows_h).pin_memory()]
-    self.ev_in = [t.cuda.Event() for _ in range(2)]
-    self.ev_done = [t.cuda.Event() for _ in range(2)]
-    self.ev_out = [t.cuda.Event() for _ in range(2)]
-    for k in range(2):
-      self.h_ids[k].copy_(ids_h[k])
-      self.h_grad[k].copy_(grads_h[k])
-    t.cuda.synchronize()
-    self.e2e = [self._capture(lambda k=k: self.padded.run(self.h_ids[k], self.h_grad[k],
-                                                          out=self.h_out[k])) for k in range(2)]
-    main = t.cuda.current_stream(self.dev)
-    for k in range(2):
-      self.ev_done[k].record(main)
-      self.ev_out[k].record(main)
-    self.e2e_i = 0
-
-  def finish_host(self):
-    main = self.torch.cuda.current_stream(self.dev)
-    main.wait_stream(self.s_h2d)
-    main.wait_stream(self.s_d2h)
-
-  def step_host(self, i):
-    t = self.torch
-    k = self.e2e_i & 1
-    self.e2e_i += 1
-    j = i % len(self.ids_h)
-    main = t.cuda.current_stream(self.dev)
-    with t.cuda.stream(self.s_h2d):
-      self.s_h2d.wait_event(self.ev_done[k])       # slot k's previous step no longer reads it
-      self.h_ids[k].copy_(self.ids_h[j], non_blocking=True)
-      self.h_grad[k].copy_(self.grads_h[j], non_blocking=True)
-      self.ev_in[k].record(self.s_h2d)
-    main.wait_event(self.ev_in[k])
-    main.wait_event(self.ev_out[k])                # slot k's rows have been drained to the host
-    if self.e2e[k] is not None:
-      self.e2e[k].replay()
-    else:
-      self.padded.run(self.h_ids[k], self.h_grad[k], out=self.h_out[k])
-    self.steps_done += 1
-    self.ev_done[k].record(main)
-    with t.cuda.stream(self.s_d2h):
-      self.s_d2h.wait_event(self.ev_done[k])
-      self.rows_host[k].copy_(self.h_out[k], non_blocking=True)
-      self.ev_out[k].record(self.s_d2h)
