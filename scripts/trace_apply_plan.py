@@ -35,6 +35,14 @@ ops.kv_variable_apply_plan(ops.OPT_GROUP_ADAM_V4, st.var, st.slot, None, plan, g
 torch.cuda.synchronize()
 lib.kv_debug_set_trace(None)
 raw = tb.cpu().numpy()
+gt = raw[131072:131072 + 2960 * 16].reshape(-1, 16)
+gt = gt[(gt[:, 0] > 0) & (gt[:, 15] > 0)]
+if len(gt):
+  d = lambda a, b: np.percentile(gt[:, b] - gt[:, a], [10, 50, 90]).round()
+  print("light group (first per warp), ns p10/p50/p90: phase1", d(0, 1), "round0", d(1, 2), "round1", d(2, 3),
+        "round2", d(3, 4), "round3", d(4, 5), "phase3", d(5, 15), "total", d(0, 15), "n", len(gt))
+  print("  round 0: issue loads", d(1, 8), "loads land", d(8, 9), "math", d(9, 10), "stores+flags", d(10, 2))
+raw[131072:] = 0
 t = raw.reshape(-1, 4)
 nw = 20
 t = t[: (len(t) // nw) * nw]

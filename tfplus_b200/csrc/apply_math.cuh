@@ -391,6 +391,9 @@ struct GradSrc {
   unsigned* ready = nullptr;
   unsigned ready_n = 0;
   int gstride = 0;
+#ifdef KVHBM_TRACE
+  unsigned long long* trace = nullptr;   // [16] timestamps of one group (tuning aid)
+#endif
 };
 
 template <int NW, int VEC, int CPL>
@@ -402,6 +405,7 @@ struct ApplySmem {
   int modes[NW][32];          // vm | am << 8 | bm << 16 (each + 1, so SKIP = 0)
   int goff[NW][32];
   int gcnt[NW][32];
+  int gpos[NW][32][4];        // the id's first four occurrence positions (planned gradients)
   unsigned char res[NW][32];  // bit0 v_under, bit1 a_under, bit2 b_under, bit3 black
   float zs[NW][32 * CPL * VEC];
 };
@@ -433,6 +437,12 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   const bool planned = gs.counts != nullptr;
   const long long i = base + lane;
   const bool valid = lane < kpw && i < n;
+#ifdef KVHBM_TRACE
+#define KV_STAMP(k) do { if (gs.trace && lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); gs.trace[k] = t_; } } while (0)
+#else
+#define KV_STAMP(k) do { } while (0)
+#endif
+  KV_STAMP(0);
 
   // ---------------- phase 1 ----------------
   long long key = 0;
@@ -445,10 +455,15 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   bool mine = valid;
   const long long ii = (valid && gs.remap) ? (long long)gs.remap[i] : i;   // index into ids / hint
   if (valid) key = ids[ii];
+  int gp4[4] = {0, 0, 0, 0};
   if (valid && planned) {
     gcnt = gs.counts[i];
     goff = gs.seg_off[i];
     if (!take_heavy && gcnt > gs.heavy_t) mine = false;
+    if (mine) {   // the first occurrences' positions now, so that phase 2 starts with the row loads
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gp4[j] = j < gcnt ? __ldg(gs.pos + goff + j) : 0;
+    }
   }
   if (mine && key != KEY_PAD) {  // padding ids of the shard exchange are skipped
     Probe pv = probe_begin(var, key), pa = probe_begin(sa, key), pb = probe_begin(sb, key);
@@ -513,7 +528,12 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   sm.modes[wib][lane] = (vmode + 1) | ((amode + 1) << 8) | ((bmode + 1) << 16);
   sm.goff[wib][lane] = goff;
   sm.gcnt[wib][lane] = gcnt;
+  if (planned) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm.gpos[wib][lane][j] = gp4[j];
+  }
   __syncwarp();
+  KV_STAMP(1);
 
   // ---------------- phase 2 ----------------
   float* zs = &sm.zs[wib][tq * tpr * CPL * VEC];
@@ -590,7 +610,8 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
 #pragma unroll
             for (int j = 0; j < GU; ++j) {
               if (k0 + j < cnt) {
-                const float* gp = gs.grad + (long long)__ldg(pl + k0 + j) * dim;
+                const int pz = (GU == 4 && k0 == 0) ? sm.gpos[wib][kl][j] : __ldg(pl + k0 + j);
+                const float* gp = gs.grad + (long long)pz * dim;
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                   const int off = (q * tpr + tl) * VEC;
@@ -611,6 +632,14 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
         }
       }
     }
+#ifdef KVHBM_TRACE
+    if (it == 0 && gs.trace) {   // loads issued / loads landed (forced) / math done
+      KV_STAMP(8);
+      float sink = g[0][0].v[0] + w[0][0].v[0] + s[0][0][0].v[0] + s[0][PARTS - 1][0].v[0];
+      if (sink == 1.2345e-30f) gs.trace[14] = 1;
+      KV_STAMP(9);
+    }
+#endif
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       if (it + u >= steps) continue;  // uniform across the warp
@@ -619,6 +648,9 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
       bool vbig, abig, bbig, black;
       row_update<VEC, CPL, KIND>(p, dim, tpr, tl, tq * tpr, zs, vm[u], g[u], w[u], s[u], &vbig,
                                  &abig, &bbig, &black);
+#ifdef KVHBM_TRACE
+      if (it == 0 && gs.trace) { if (vbig && black && w[u][0].v[0] == 1.2345e-30f) gs.trace[14] = 2; KV_STAMP(10); }
+#endif
 #pragma unroll
       for (int q = 0; q < CPL; ++q) {
         const int off = (q * tpr + tl) * VEC;
@@ -640,6 +672,7 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
         sm.res[wib][kl] = (((vb >> sh) & tmask) == 0 ? 1 : 0) | (((ab >> sh) & tmask) == 0 ? 2 : 0) |
                           (((bb >> sh) & tmask) == 0 ? 4 : 0) | (black ? 8 : 0);
     }
+    KV_STAMP(2 + (it < 12 ? it : 12));
   }
   __syncwarp();
 
@@ -681,6 +714,8 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   }
   __syncwarp();
   if (gs.ready && valid) gs.ready[i - gs.row0] = 0u;   // every tile is past its wait
+  KV_STAMP(15);
+#undef KV_STAMP
 }
 
 }  // namespace kvhbm

@@ -369,6 +369,10 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
     for (;;) {
       const long long base = next_light_group(pl.work, kpw, lane);
       if (base >= U) break;
+#ifdef KVHBM_TRACE
+      if (trace && n_groups == 0) gs.trace = trace + 131072 + ((size_t)blockIdx.x * AP_NW + wib) * 16;
+      else gs.trace = nullptr;
+#endif
       apply_group<AP_NW, VEC, CPL, KIND, 1, 4>(sm, wib, var, sa, sb, ids, gs, base, U, p, today, tpr,
                                                kpw, false);
 #ifdef KVHBM_TRACE
@@ -542,10 +546,15 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
   const int sms = sm_count(var->device);
   const int kpi = 32 / tpr;
   // light warps of a full grid; a Zipf batch has ~n/3 distinct ids
+  // Light groups are latency chains: ~3 us of probes, then per round of 32 / tpr ids ~1.8 us for
+  // the gradient rows and ~2 us of row math (measured, scripts/trace_apply_plan.py).  Small
+  // groups balance best over the dynamic counter (measured at the microbench: 2 rounds per
+  // group 50 us, 4 rounds 54-70, 6 rounds 83, 8 rounds 95); they only grow when there would be
+  // more than four groups per warp.  A Zipf batch has ~n/3 distinct ids.
   const long long lwarps = (long long)sms * bps_env * AP_NW;
   const long long n_est = (pv.n + 2) / 3;
-  int kpw = kpi;
-  while (kpw < 32 && (n_est + kpw - 1) / kpw > lwarps) kpw <<= 1;
+  int kpw = 2 * kpi;
+  while (kpw + kpi <= 32 && (n_est + kpw - 1) / kpw > 4 * lwarps) kpw += kpi;
   if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
   long long blocks = ((pv.n + kpw - 1) / kpw + AP_NW - 1) / AP_NW;
   if (blocks > (long long)sms * bps_env) blocks = (long long)sms * bps_env;
