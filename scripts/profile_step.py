@@ -26,8 +26,9 @@ st.populate()
 ids_np, grads_np = bench.make_batches(min(4, args.steps), args.keys, args.batch, args.dim)
 ids = [torch.from_numpy(x).to(dev) for x in ids_np]
 grads = [torch.from_numpy(x).to(dev) for x in grads_np]
-buf = st.new_buffers()
+plan = ops.Plan(args.batch, dev)
+rows = torch.empty((args.batch, args.dim), dtype=torch.float32, device=dev)
 for i in range(args.steps):
-  st.step_eager(ids[i % len(ids)], grads[i % len(ids)], buf)
+  st.step_eager(ids[i % len(ids)], grads[i % len(ids)], plan, rows)
 torch.cuda.synchronize()
 print("done")

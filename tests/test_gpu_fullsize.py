@@ -141,8 +141,11 @@ def _export_state(st):
 
 
 def test_rotation_graph_equals_step_by_step_and_oracle():
-  """bench.py's pipelined schedule (one graph per rotation, only true dependencies between
-  consecutive steps) leaves the tables as running the steps one after the other does."""
+  """bench.py's timed schedule (one graph per rotation: lookup -> fused gradient sum + apply ->
+  next lookup on one stream, the dedup plan of the next batch built beside it) leaves the
+  tables EXACTLY as running the steps strictly one after the other does - the gradient sums
+  are added in TF's order, nothing depends on scheduling - and both equal the oracle run over
+  the same steps at the north-star's 1e-6, slot rows (m, v, linear) included."""
   keys, D, B, nb = 30000, 64, 4096, bench.N_BATCHES
   dev = torch.device(DEV)
   ids_np, grads_np = bench.make_batches(nb, keys, B, D, seed_ids=5, seed_grad=6)
@@ -159,26 +162,18 @@ def test_rotation_graph_equals_step_by_step_and_oracle():
       st.run_steps(2 * nb + 3)                                      # 2 rotations + 3 single steps
     torch.cuda.synchronize()
     states.append(_export_state(st))
-    rows.append([b["rows"].cpu().numpy().copy() for b in st.bufs])
+    rows.append([r.cpu().numpy().copy() for r in st.rows])
     hp = st.hp.cpu().numpy().copy()
     ops.destroy_kv_variable_op_v2(st.var)
     ops.destroy_kv_variable_op_v2(st.slot)
   (va, sa, _), (vb, sb, _) = states
   assert va.keys() == vb.keys() and sa.keys() == sb.keys()
-  # Not bit for bit: the gradient sums add rows with float atomics, whose order varies from
-  # launch to launch, and 51 Adam steps with group-lasso thresholds amplify that rounding noise
-  # (DESIGN.md section 3).  A missing dependency would show up at the size of an update: 1e-3
-  # absolute on the values, 1e-1 on the slots.
   ks = sorted(va)
-  A, Bv = np.stack([va[k] for k in ks]), np.stack([vb[k] for k in ks])
-  SA, SB = np.stack([sa[k] for k in ks]), np.stack([sb[k] for k in ks])
-  print("strict vs rotation: max |dvar| %.3g, max |dslot| %.3g"
-        % (np.abs(A - Bv).max(), np.abs(SA - SB).max()))
-  np.testing.assert_allclose(A, Bv, rtol=1e-3, atol=2e-5)
-  np.testing.assert_allclose(SA, SB, rtol=1e-3, atol=1e-4)
+  np.testing.assert_array_equal(np.stack([va[k] for k in ks]), np.stack([vb[k] for k in ks]))
+  np.testing.assert_array_equal(np.stack([sa[k] for k in ks]), np.stack([sb[k] for k in ks]))
   for ra, rb in zip(*rows):
-    np.testing.assert_allclose(ra, rb, rtol=1e-3, atol=2e-5)
-  # and both equal the oracle run over the same 3 * nb + 3 steps (1e-6)
+    np.testing.assert_array_equal(ra, rb)
+  # and both equal the oracle run over the same 3 * nb + 3 steps
   var = ob.OracleTable(D, 0, seed=1)
   var.set_init_table(bench.init_table(D))
   slot = ob.OracleTable(3 * D, 0, seed=1)
@@ -198,12 +193,13 @@ def test_rotation_graph_equals_step_by_step_and_oracle():
                            h["l21"], today=TODAY)
     b1p, b2p = b1p * np.float32(h["beta1"]), b2p * np.float32(h["beta2"])
   assert hp[1] == b1p and hp[2] == b2p
-  ref = var.export(first_n=6, enable_cutoff=False, cutoff_value=0.0, freq_u32=True)
-  ref_rows = dict(zip(ref["keys"].tolist(), ref["values"]))
-  assert ref_rows.keys() == vb.keys()
-  got = np.stack([vb[k] for k in sorted(vb)])
-  want = np.stack([ref_rows[k] for k in sorted(vb)])
-  print("rotation vs oracle: max |dvar| %.3g" % np.abs(got - want).max())
-  np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-5)
-  np.testing.assert_allclose(rows[1][(3 * nb + 2) % nb], last_rows.reshape(B, D), rtol=1e-3,
-                             atol=2e-5)
+  for got_map, otab, name in ((vb, var, "var"), (sb, slot, "m_v_linear")):
+    ref = otab.export(first_n=6, enable_cutoff=False, cutoff_value=0.0, freq_u32=True)
+    ref_rows = dict(zip(ref["keys"].tolist(), ref["values"]))
+    assert ref_rows.keys() == got_map.keys()
+    got = np.stack([got_map[k] for k in sorted(got_map)])
+    want = np.stack([ref_rows[k] for k in sorted(got_map)])
+    print("rotation vs oracle, %s: max |d| %.3g" % (name, np.abs(got - want).max()))
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7, err_msg=name)
+  np.testing.assert_allclose(rows[1][(3 * nb + 2) % nb], last_rows.reshape(B, D), rtol=1e-6,
+                             atol=1e-7)

@@ -366,9 +366,11 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
     GradSrc gs;
     gs.grad = grad; gs.row0 = 0; gs.counts = pl.counts; gs.seg_off = pl.seg_off; gs.pos = pl.pos;
     gs.heavy_t = pl.heavy_t; gs.hint = pl.hint; gs.cg = false;
+    const long long ngroups = (U + kpw - 1) / kpw;
+    gs.stride = ngroups;
     for (;;) {
-      const long long base = next_light_group(pl.work, kpw, lane);
-      if (base >= U) break;
+      const long long base = next_light_group(pl.work, 1, lane);   // group g: ids g, g + G, g + 2G, ...
+      if (base >= ngroups) break;
 #ifdef KVHBM_TRACE
       if (trace && n_groups == 0) gs.trace = trace + 131072 + ((size_t)blockIdx.x * AP_NW + wib) * 16;
       else gs.trace = nullptr;
@@ -553,7 +555,7 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
   // more than four groups per warp.  A Zipf batch has ~n/3 distinct ids.
   const long long lwarps = (long long)sms * bps_env * AP_NW;
   const long long n_est = (pv.n + 2) / 3;
-  int kpw = 2 * kpi;
+  int kpw = 2 * kpi <= 32 ? 2 * kpi : kpi;
   while (kpw + kpi <= 32 && (n_est + kpw - 1) / kpw > 4 * lwarps) kpw += kpi;
   if (kpw_env >= kpi && kpw_env <= 32) kpw = kpw_env;
   long long blocks = ((pv.n + kpw - 1) / kpw + AP_NW - 1) / AP_NW;
