@@ -108,10 +108,17 @@ int kv_insert_or_update(kv_table* t, const int64_t* d_ids, const float* d_values
                         int64_t n, const uint8_t* d_filter_out,
                         const uint8_t* d_blacklist, kv_stream stream);
 /* KvVariableScatterUpdateOP<op>, kernels/kv_variable_ops.cc:1097-1163 ->
- * KvVariable::ScatterUpdate kernels/kv_variable.h:616-734.  Ids must be unique
- * (TF dedups before the optimizer reaches this op). */
+ * KvVariable::ScatterUpdate kernels/kv_variable.h:616-734.  The ids may repeat
+ * (GradientDescentOptimizer._resource_apply_sparse_duplicate_indices calls scatter_add with
+ * the raw indices): every occurrence is applied, those of one key one after the other in
+ * index order.  The call dedups the ids internally (a dedup plan kept with the table, sized on
+ * first use - not under CUDA-graph capture). */
 int kv_scatter(kv_table* t, int op, const int64_t* d_ids, const float* d_updates,
                int64_t n, kv_stream stream);
+/* The same for ids the caller KNOWS to be distinct (after TF's _deduplicate_indexed_slices:
+ * the tfplus-Adam path, python/training/adam.py:131,157): no dedup pass. */
+int kv_scatter_unique(kv_table* t, int op, const int64_t* d_ids, const float* d_updates,
+                      int64_t n, kv_stream stream);
 /* KvVariable::GetCount / GetTimeStamp, kernels/kv_variable.h:503-561 (ops
  * KvVariableGetCountV2 / KvVariableGetTimeStamp have no kernel in the OSS tree). */
 int kv_get_count(kv_table* t, const int64_t* d_ids, int64_t n, int32_t* d_out,

@@ -59,6 +59,9 @@ def lib():
       "kvo_apply_adagrad": (None, [vp, vp, P, P, i64, f32, C.c_int, u16]),
       "kvo_apply_group_adam_v4": (None, [vp, vp, P, P, i64] + [f32] * 9 + [u16]),
       "kvo_apply_sparse_group_ftrl": (None, [vp, vp, vp, P, P, i64] + [f32] * 6 + [u16]),
+      "kvo_apply_group_adam_v3": (None, [vp, vp, P, P, i64] + [f32] * 9 + [u16]),
+      "kvo_apply_sparse_ftrl_v2": (None, [vp, vp, vp, P, P, i64] + [f32] * 5 + [u16]),
+      "kvo_apply_group_sparse_ftrl_v2": (None, [vp, vp, vp, P, P, i64] + [f32] * 5 + [u16]),
       "kvo_adam_step": (None, [vp, vp, P, P, i64] + [f32] * 6 + [u16]),
       "kvo_get_count": (None, [vp, P, i64, P]),
       "kvo_get_timestamp": (None, [vp, P, i64, P, u16]),
@@ -277,6 +280,31 @@ def apply_sparse_group_ftrl(var, accum, linear, ids, grad, lr, l1, l2, l21,
   lib().kvo_apply_sparse_group_ftrl(var._h, accum._h, linear._h, _p(ids), _p(grad),
                                     ids.size, lr, l1, l2, l21, l2_shrinkage,
                                     lr_power, today)
+
+
+def apply_group_adam_v3(var, m_v_linear, ids, grad, lr, beta1_power, beta2_power,
+                        beta1, beta2, epsilon, l1, l2, l21, today=0):
+  ids = _ids(ids)
+  grad = _f32(grad).reshape(ids.size, var.dim)
+  lib().kvo_apply_group_adam_v3(var._h, m_v_linear._h, _p(ids), _p(grad), ids.size,
+                                lr, beta1_power, beta2_power, beta1, beta2, epsilon,
+                                l1, l2, l21, today)
+
+
+def apply_sparse_ftrl_v2(var, accum, linear, ids, grad, lr, l1, l2, l2_shrinkage=0.0,
+                         lr_power=-0.5, today=0):
+  ids = _ids(ids)
+  grad = _f32(grad).reshape(ids.size, var.dim)
+  lib().kvo_apply_sparse_ftrl_v2(var._h, accum._h, linear._h, _p(ids), _p(grad), ids.size,
+                                 lr, l1, l2, l2_shrinkage, lr_power, today)
+
+
+def apply_group_sparse_ftrl_v2(var, accum, linear, ids, grad, lr, l1, l2, l2_shrinkage=0.0,
+                               lr_power=-0.5, today=0):
+  ids = _ids(ids)
+  grad = _f32(grad).reshape(ids.size, var.dim)
+  lib().kvo_apply_group_sparse_ftrl_v2(var._h, accum._h, linear._h, _p(ids), _p(grad),
+                                       ids.size, lr, l1, l2, l2_shrinkage, lr_power, today)
 
 
 def adam_step(var, m_v, ids, grad, lr, beta1, beta2, epsilon, beta1_power,

@@ -860,6 +860,170 @@ void kvo_apply_sparse_group_ftrl(void* hvar, void* hacc, void* hlin,
   });
 }
 
+// KvVariableGroupSparseApplyAdamV3Op, training_ops.cc:5840-5927: as V4, but nothing is
+// pre-scaled by lr (:5846-5849) - lr divides the curvature terms of `linear` and of the
+// denominator instead (:5893-5916).  PARITY UNPINNED: no reference test runs this op.
+void kvo_apply_group_adam_v3(void* hvar, void* hmvl, const int64_t* ids,
+                             const float* grad, int64_t n, float lr,
+                             float beta1_power, float beta2_power, float beta1,
+                             float beta2, float epsilon, float l1, float l2,
+                             float l21, uint16_t today) {
+  Table* var = static_cast<Table*>(hvar);
+  Table* mvl = static_cast<Table*>(hmvl);
+  const int D = var->dim;
+  const float alpha = std::sqrt(1.0f - beta2_power) / (1.0f - beta1_power);   // :5846-5848
+  const float l21_norm = l21 * std::sqrt(static_cast<float>(D));              // :5849
+  const bool later_step = beta1 > beta1_power;                                // :5899
+  Pool::Get().ParallelFor(n, 5000, [&](int64_t s, int64_t e) {
+    std::vector<float> z(D), sq(D);
+    for (int64_t i = s; i < e; ++i) {
+      const int64_t key = ids[i];
+      Segment& sg = var->SegOf(key);
+      sg.mu.lock();
+      bool filt = false;
+      EmbeddingValue *ev, *es;
+      float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
+      if (filt) { sg.mu.unlock(); continue; }
+      float* o = mvl->FindOrInsertUnsafe(key, nullptr, today, &es);
+      float* m = o;
+      float* v = o + D;
+      float* lin = o + 2 * D;
+      const float* g = grad + i * D;
+      for (int j = 0; j < D; ++j) {
+        m[j] = beta1 * m[j] + (1.0f - beta1) * g[j];
+        const float nv = beta2 * v[j] + (1.0f - beta2) * (g[j] * g[j]);
+        const float s_nv = std::sqrt(nv);
+        sq[j] = s_nv;
+        if (later_step)
+          lin[j] += alpha * m[j] - (s_nv - std::sqrt(v[j])) / lr * w[j];
+        else
+          lin[j] += alpha * m[j] - (s_nv - std::sqrt(v[j]) + epsilon) / lr * w[j];
+        const float adj = MaxF(MinF(lin[j], l1), -l1);
+        z[j] = adj - lin[j];
+      }
+      const float nrm = std::sqrt(EigenSumSquares(z.data(), D));
+      if (nrm > l21_norm) {
+        const float c = 1.0f - l21_norm / nrm;
+        for (int j = 0; j < D; ++j) {
+          const float y = (sq[j] + epsilon) / lr + 2.0f * l2;
+          w[j] = z[j] * c / y;
+        }
+        var->UpdateUnderThreshold(ev, w);
+      } else {
+        var->MarkBlacklistUnsafe(sg, key, ev);
+      }
+      for (int j = 0; j < D; ++j)
+        v[j] = beta2 * v[j] + (1.0f - beta2) * (g[j] * g[j]);
+      mvl->UpdateUnderThreshold(es, o);
+      sg.mu.unlock();
+    }
+  });
+}
+
+// KvVariableSparseApplyFtrlOp<has_l2_shrinkage=true> = op KvVariableSparseApplyFtrlV2,
+// training_ops.cc:430-489: FTRL-proximal per row; no group lasso, no blacklist, no
+// CoverUpdateUnsafe (the under-threshold flags stay as the insert left them).  With
+// l2_shrinkage = 0 this is TF's ResourceSparseApplyFtrlV2, which the reference's own test
+// pins at 1e-8 (py_ut/tests/test_training_ops.py:68-205; restated in tests/test_oracle_kat.py).
+void kvo_apply_sparse_ftrl_v2(void* hvar, void* hacc, void* hlin, const int64_t* ids,
+                              const float* grad, int64_t n, float lr, float l1, float l2,
+                              float l2_shrinkage, float lr_power, uint16_t today) {
+  Table* var = static_cast<Table*>(hvar);
+  Table* acc = static_cast<Table*>(hacc);
+  Table* lint = static_cast<Table*>(hlin);
+  const int D = var->dim;
+  const bool fast = (lr_power == -0.5f);
+  auto P = [fast, lr_power](float x) { return fast ? std::sqrt(x) : std::pow(x, -lr_power); };
+  Pool::Get().ParallelFor(n, 5000, [&](int64_t s, int64_t e) {
+    for (int64_t i = s; i < e; ++i) {
+      const int64_t key = ids[i];
+      Segment& sg = var->SegOf(key);
+      sg.mu.lock();
+      bool filt = false;
+      EmbeddingValue *ev, *el, *ea;
+      float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
+      if (filt) { sg.mu.unlock(); continue; }
+      float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
+      float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      const float* g = grad + i * D;
+      for (int j = 0; j < D; ++j) {
+        // every statement of COMPUTE_FTRL is elementwise, so the lazy expressions can be
+        // followed coefficient by coefficient: grad_to_use is re-read with the NEW var by the
+        // last statement (:477)
+        const float gs = g[j] + (2.0f * l2_shrinkage) * w[j];
+        const float na = a[j] + gs * gs;
+        const float pna = P(na);
+        lin[j] += gs - (pna - P(a[j])) / lr * w[j];
+        const float x = MaxF(MinF(lin[j], l1), -l1) - lin[j];
+        const float y = pna / lr + 2.0f * l2;
+        w[j] = x / y;
+        const float g2 = g[j] + (2.0f * l2_shrinkage) * w[j];
+        a[j] += g2 * g2;
+      }
+      sg.mu.unlock();
+    }
+  });
+}
+
+// KvVariableGroupSparseApplyFtrlOp<has_l2_shrinkage=true> = op KvVariableGroupSparseApplyFtrlV2,
+// training_ops.cc:960-1013: the group lasso acts on the norm of `linear` itself with
+// threshold l1 (:985-998); `accum += grad_to_use.square()` appears TWICE in the macro
+// (:1007-1008) and is restated as written.  PARITY UNPINNED: no reference test runs this op.
+void kvo_apply_group_sparse_ftrl_v2(void* hvar, void* hacc, void* hlin, const int64_t* ids,
+                                    const float* grad, int64_t n, float lr, float l1,
+                                    float l2, float l2_shrinkage, float lr_power,
+                                    uint16_t today) {
+  Table* var = static_cast<Table*>(hvar);
+  Table* acc = static_cast<Table*>(hacc);
+  Table* lint = static_cast<Table*>(hlin);
+  const int D = var->dim;
+  const bool fast = (lr_power == -0.5f);
+  auto P = [fast, lr_power](float x) { return fast ? std::sqrt(x) : std::pow(x, -lr_power); };
+  Pool::Get().ParallelFor(n, 5000, [&](int64_t s, int64_t e) {
+    std::vector<float> pna(D), gs(D), l2v(D);
+    for (int64_t i = s; i < e; ++i) {
+      const int64_t key = ids[i];
+      Segment& sg = var->SegOf(key);
+      sg.mu.lock();
+      bool filt = false;
+      EmbeddingValue *ev, *el, *ea;
+      float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
+      if (filt) { sg.mu.unlock(); continue; }
+      float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
+      float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      const float* g = grad + i * D;
+      for (int j = 0; j < D; ++j) {
+        gs[j] = g[j] + (2.0f * l2_shrinkage) * w[j];
+        const float na = a[j] + gs[j] * gs[j];
+        pna[j] = P(na);
+        lin[j] += gs[j] - (pna[j] - P(a[j])) / lr * w[j];
+        l2v[j] = lin[j];
+      }
+      const float nrm = std::sqrt(EigenSumSquares(l2v.data(), D));
+      bool blacklisted = false;
+      if (nrm > l1) {
+        for (int j = 0; j < D; ++j) {
+          const float eta_rec = pna[j] / lr;
+          const float coef = (l1 - nrm) / ((eta_rec + 2.0f * l2) * nrm);
+          w[j] = coef * lin[j];
+        }
+        var->UpdateUnderThreshold(ev, w);
+      } else {
+        var->MarkBlacklistUnsafe(sg, key, ev);
+        blacklisted = true;
+      }
+      for (int j = 0; j < D; ++j) {
+        const float g2 = blacklisted ? gs[j] : g[j] + (2.0f * l2_shrinkage) * w[j];
+        a[j] += g2 * g2;
+        a[j] += g2 * g2;
+      }
+      lint->UpdateUnderThreshold(el, lin);
+      acc->UpdateUnderThreshold(ea, a);
+      sg.mu.unlock();
+    }
+  });
+}
+
 // tfplus AdamOptimizer._tfplus_apply_sparse_shared, python/training/adam.py:93-163,
 // concatenated-slot layout [m | v] (adam.py:83-86,100-109): gather(m_v) is a
 // GatherOrInsert on the slot table, then separately rounded TF elementwise ops,

@@ -242,6 +242,105 @@ def test_sparse_group_ftrl(dim, l1, l2, l21, l2s, lrp):
   lin.check_state(**tol)
 
 
+@pytest.mark.parametrize("dim,l1,l2,l21", [(64, 0., 0., 0.), (64, 1e-4, 1e-3, 1e-4), (16, 1e-3, 1e-2, 1e-2),
+                                           (1, 0., 0., 0.)])
+def test_group_adam_v3(dim, l1, l2, l21):
+  # KvVariableGroupSparseApplyAdamV3 (training_ops.cc:5840-5927)
+  var = Pair(dim, enter_threshold=2)
+  slot = Pair(3 * dim, init=0.0)
+  b1, b2, lr, eps = 0.9, 0.999, 1e-2, 1e-8
+  b1p, b2p = b1, b2
+  for ids, u, g in _steps(6, 2000, 3000, dim, seed=300 + dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_group_sparse_apply_adam_v3(var.gpu, slot.gpu, t(g), t(u), lr, b1p, b2p, b1, b2,
+                                               eps, l1, l2, l21)
+    ob.apply_group_adam_v3(var.cpu, slot.cpu, u, g, lr, b1p, b2p, b1, b2, eps, l1, l2, l21,
+                           today=TODAY)
+    b1p *= b1
+    b2p *= b2
+    var.check_state(rtol=RTOL, atol=ATOL)
+  slot.check_state(rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dim,l1,l2,l2s", [(64, 0., 0., 0.), (16, 0.05, 0.1, 0.), (32, 1e-3, 1e-3, 1e-3),
+                                           (1, 0.01, 0., 0.)])
+def test_sparse_apply_ftrl_v2(dim, l1, l2, l2s):
+  # KvVariableSparseApplyFtrlV2 (training_ops.cc:430-489): no blacklist, flags untouched
+  var = Pair(dim, enter_threshold=1)
+  acc = Pair(dim, init=0.1)
+  lin = Pair(dim, init=0.0)
+  for ids, u, g in _steps(5, 1500, 2500, dim, seed=400 + dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_sparse_apply_ftrl_v2(var.gpu, acc.gpu, lin.gpu, t(g), t(u), 0.1, l1, l2, l2s, -0.5)
+    ob.apply_sparse_ftrl_v2(var.cpu, acc.cpu, lin.cpu, u, g, 0.1, l1, l2, l2s, -0.5, today=TODAY)
+  _, cs = var.check_state(rtol=RTOL, atol=ATOL)
+  assert len(cs["black"]) == 0
+  acc.check_state(rtol=RTOL, atol=ATOL)
+  lin.check_state(rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dim,l1,l2,l2s", [(64, 0., 0., 0.), (16, 2.0, 0.1, 0.), (32, 0.5, 1e-3, 1e-3)])
+def test_group_sparse_apply_ftrl_v2(dim, l1, l2, l2s):
+  # KvVariableGroupSparseApplyFtrlV2 (training_ops.cc:960-1013): lasso on ||linear|| vs l1
+  var = Pair(dim, enter_threshold=1)
+  acc = Pair(dim, init=0.1)
+  lin = Pair(dim, init=0.0)
+  n_black = 0
+  for ids, u, g in _steps(5, 1500, 2500, dim, seed=500 + dim):
+    var.gather_or_insert(ids, exact=False)
+    ops.kv_variable_group_sparse_apply_ftrl_v2(var.gpu, acc.gpu, lin.gpu, t(g), t(u), 0.1, l1, l2, l2s,
+                                               -0.5)
+    ob.apply_group_sparse_ftrl_v2(var.cpu, acc.cpu, lin.cpu, u, g, 0.1, l1, l2, l2s, -0.5,
+                                  today=TODAY)
+    _, cs = var.check_state(rtol=RTOL, atol=ATOL)
+    n_black = max(n_black, len(cs["black"]))
+  acc.check_state(rtol=RTOL, atol=ATOL)
+  lin.check_state(rtol=RTOL, atol=ATOL)
+  if l1 >= 0.5:
+    assert n_black > 10
+
+
+def test_get_count_and_get_timestamp():
+  # KvVariable::GetCount / GetTimeStamp, kv_variable.h:503-561: lo16 count and hi16 day of the
+  # frequency word; an absent key counts 0 and reports the current day (:552-553)
+  p = Pair(8)
+  ids = np.array([5, 9, 5, 11, 5], np.int64)
+  p.gather_or_insert(ids)
+  ops.set_today(TODAY + 3)
+  ops.kv_variable_gather_or_insert_v2(p.gpu, t(np.array([9], np.int64)))
+  p.cpu.gather_or_insert(np.array([9], np.int64), today=TODAY + 3)
+  q = np.array([5, 9, 11, 12345], np.int64)
+  got_c = ops.kv_variable_get_count_v2(p.gpu, t(q)).cpu().numpy()
+  got_t = ops.kv_variable_get_time_stamp(p.gpu, t(q)).cpu().numpy()
+  np.testing.assert_array_equal(got_c, p.cpu.get_count(q))
+  np.testing.assert_array_equal(got_t.view(np.uint32), p.cpu.get_timestamp(q, today=TODAY + 3))
+  assert got_c.tolist() == [3, 2, 1, 0]
+  assert got_t.tolist() == [TODAY, TODAY + 3, TODAY, TODAY + 3]
+  ops.set_today(TODAY)
+
+
+def test_scatter_with_duplicate_ids():
+  # GradientDescentOptimizer._resource_apply_sparse_duplicate_indices hands scatter_add the raw
+  # indices: ScatterUpdate (kv_variable.h:616-734) applies every occurrence, on new and on
+  # existing keys alike
+  dim = 16
+  p = Pair(dim, init=0.5)
+  p.gather_or_insert(np.arange(50, dtype=np.int64))
+  rng = np.random.default_rng(77)
+  ids = rng.integers(0, 100, size=4000).astype(np.int64)      # ~40 occurrences per key, half new
+  upd = rng.integers(-4, 5, size=(4000, dim)).astype(np.float32) * 0.25   # sums are exact
+  p.scatter("add", ids, upd)
+  p.check_state()
+  p.scatter("sub", ids[:1000], upd[:1000])
+  p.check_state()
+  last = {}
+  for i, k in enumerate(ids.tolist()):
+    last[k] = i
+  keep = np.array(sorted(last.values()))
+  p.scatter("update", ids[keep], upd[keep])                     # unique ids: defined result
+  p.check_state()
+
+
 def test_adam_scatter_path_is_bit_exact():
   # the reference's own Adam route: gather(m_v) + torch elementwise + scatter_update + scatter_sub
   dim = 32

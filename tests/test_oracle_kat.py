@@ -237,6 +237,74 @@ def test_sparse_group_ftrl_l21_zero_equals_ftrl():
   np.testing.assert_allclose(lin.gather_or_zeros(ids), rl, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("l1,l2", [(0.0, 0.0), (0.05, 0.1)])
+def test_sparse_apply_ftrl_v2_equals_tf_ftrl(l1, l2):
+  # py_ut/tests/test_training_ops.py:68-205: KvVariableSparseApplyFtrlV2 == TF ftrl_v2 at atol
+  # 1e-8, three steps of 300x64 N(0,1) grads on var 0.03, accum 0.1, linear 0.0, lr 0.01
+  # (l2_shrinkage 0: the two formulas only differ in what they square into accum otherwise)
+  n, dim = 300, 64
+  rng = np.random.default_rng(16)
+  var = _table(dim=dim, init=np.full((R, dim), 0.03, np.float32))
+  acc = _table(dim=dim, init=np.full((R, dim), 0.1, np.float32))
+  lin = _table(dim=dim, init=np.zeros((R, dim), np.float32))
+  ids = np.arange(n)
+  rv = np.full((n, dim), 0.03, np.float32)
+  ra = np.full((n, dim), 0.1, np.float32)
+  rl = np.zeros((n, dim), np.float32)
+  for _ in range(3):
+    g = rng.normal(size=(n, dim)).astype(np.float32)
+    ob.apply_sparse_ftrl_v2(var, acc, lin, ids, g, 0.01, l1, l2, 0.0, -0.5)
+    _np_ftrl_v2(rv, ra, rl, g, 0.01, l1, l2, 0.0, -0.5)
+  np.testing.assert_allclose(var.gather_or_zeros(ids), rv, rtol=2e-6, atol=1e-6)
+  np.testing.assert_allclose(acc.gather_or_zeros(ids), ra, rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(lin.gather_or_zeros(ids), rl, rtol=2e-6, atol=2e-6)
+  # no blacklist, no filter side effects: every key is still there
+  assert var.size() == n
+
+
+def test_group_adam_v3_zero_reg_first_step_is_adam_shaped():
+  # V3 (training_ops.cc:5893-5925) with l1=l2=l21=0 on a fresh slot: linear = alpha*m -
+  # (sqrt(nv)+eps)/lr*var and var = -linear / ((sqrt(nv)+eps)/lr)  =>  var' = var - lr*alpha*m /
+  # (sqrt(nv)+eps): Adam's first step with alpha = sqrt(1-b2^t)/(1-b1^t)
+  h, dim = 10, 64
+  g = np.random.default_rng(17).random((h, dim), dtype=np.float32)
+  var = _table(dim=dim, init=np.ones((R, dim), np.float32))
+  slot = _table(dim=3 * dim, init=np.zeros((R, 3 * dim), np.float32))
+  ids = np.arange(h)
+  var.gather_or_insert(ids)
+  lr, b1, b2, eps = 0.1, 0.9, 0.999, 1e-8
+  ob.apply_group_adam_v3(var, slot, ids, g, lr, b1, b2, b1, b2, eps, 0., 0., 0.)
+  ref = np.ones((h, dim), np.float32)
+  m = np.zeros_like(ref)
+  v = np.zeros_like(ref)
+  _np_adam_step(ref, m, v, g, lr, b1, b2, eps, b1, b2)
+  np.testing.assert_allclose(var.gather_or_zeros(ids), ref, rtol=0, atol=2e-6)
+  got = slot.gather_or_zeros(ids)
+  np.testing.assert_allclose(got[:, :dim], m, rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(got[:, dim:2 * dim], v, rtol=1e-6, atol=1e-9)
+
+
+def test_group_sparse_ftrl_v2_thresholds_on_the_norm_of_linear():
+  # training_ops.cc:985-1008: ||linear|| <= l1 blacklists the key, otherwise
+  # var = (l1 - ||linear||) / ((sqrt(na)/lr + 2*l2) * ||linear||) * linear; accum gets g^2 twice
+  dim = 8
+  var = _table(dim=dim, init=np.full((R, dim), 0.03, np.float32))
+  acc = _table(dim=dim, init=np.full((R, dim), 0.1, np.float32))
+  lin = _table(dim=dim, init=np.zeros((R, dim), np.float32))
+  ids = np.arange(2)
+  g = np.stack([np.full(dim, 1e-4, np.float32), np.full(dim, 2.0, np.float32)])
+  ob.apply_group_sparse_ftrl_v2(var, acc, lin, ids, g, 0.1, 0.5, 0.01, 0.0, -0.5)
+  f = np.float32
+  assert np.array_equal(var.gather_or_zeros(ids)[0], np.zeros(dim, f))   # blacklisted: reads zeros
+  assert var.size() == 1
+  na = f(0.1) + g[1] * g[1]
+  linear = g[1] - (np.sqrt(na) - np.sqrt(f(0.1))) / f(0.1) * f(0.03)
+  nrm = np.sqrt(np.sum(linear * linear, dtype=np.float32))
+  want = (f(0.5) - nrm) / ((np.sqrt(na) / f(0.1) + f(0.02)) * nrm) * linear
+  np.testing.assert_allclose(var.gather_or_zeros(ids)[1], want, rtol=2e-6)
+  np.testing.assert_allclose(acc.gather_or_zeros(ids)[1], f(0.1) + 2 * g[1] * g[1], rtol=1e-6)
+
+
 def test_sparse_group_ftrl_differs_with_regularisers():
   # py_ut/tests/test_training_ops.py:475-543 only asserts inequality
   n, dim = 50, 64

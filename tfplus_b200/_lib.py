@@ -39,6 +39,7 @@ SIGNATURES = {
     "kv_gather_or_zeros": [vp, vp, i64, vp, vp],
     "kv_insert_or_update": [vp, vp, vp, i64, vp, vp, vp],
     "kv_scatter": [vp, i32, vp, vp, i64, vp],
+    "kv_scatter_unique": [vp, i32, vp, vp, i64, vp],
     "kv_get_count": [vp, vp, i64, vp, vp],
     "kv_get_timestamp": [vp, vp, i64, vp, u16, vp],
     "kv_apply_adagrad": [vp, vp, vp, vp, i64, vp, f32, i32, u16, vp],

@@ -27,7 +27,7 @@ void workspace_delete(Workspace*);
 
 int do_gather(Table*, bool insert, const int64_t*, const int32_t*, int64_t, float*, uint16_t,
               cudaStream_t, const int32_t* d_n = nullptr);
-int do_scatter(Table*, int op, const int64_t*, const float*, int64_t, cudaStream_t);
+int do_scatter(Table*, int op, const int64_t*, const float*, int64_t, cudaStream_t, bool unique_ids);
 int do_insert(Table*, const int64_t*, const float*, int64_t, const uint8_t*, const uint8_t*,
               cudaStream_t);
 int do_get_count(Table*, const int64_t*, int64_t, int32_t*, cudaStream_t);
@@ -234,7 +234,13 @@ int kv_scatter(kv_table* t, int op, const int64_t* d_ids, const float* d_updates
                kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_updates)), "scatter: bad arguments");
-  return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream));
+  return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream), false);
+}
+int kv_scatter_unique(kv_table* t, int op, const int64_t* d_ids, const float* d_updates, int64_t n,
+                      kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && (n == 0 || (d_ids && d_updates)), "scatter: bad arguments");
+  return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream), true);
 }
 int kv_get_count(kv_table* t, const int64_t* d_ids, int64_t n, int32_t* d_out, kv_stream stream) {
   KV_ENTER(t);

@@ -350,13 +350,13 @@ __global__ void unique_index_kernel(UScratch s, const int* __restrict__ slot_of,
 // ---- plan: segments into increasing position ---------------------------------------------
 // Light segments (<= 32 occurrences): a warp loads the segment and every lane ranks its
 // position among the others (positions are distinct, so the ranks are a permutation).
-__global__ void __launch_bounds__(256)
-plan_sort_light_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
-                       const int* __restrict__ num_unique, const int* __restrict__ pos_u,
-                       int* __restrict__ pos, int heavy_t) {
+__device__ __forceinline__ void
+plan_sort_light(const int* __restrict__ counts, const int* __restrict__ seg_off,
+                const int* __restrict__ num_unique, const int* __restrict__ pos_u,
+                int* __restrict__ pos, int heavy_t, long long block, long long nblocks) {
   const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp = (block * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (nblocks * blockDim.x) >> 5;
   const int U = *num_unique;
   for (long long r0 = warp * 32; r0 < U; r0 += nwarps * 32) {
     const long long r = r0 + lane;
@@ -387,18 +387,18 @@ plan_sort_light_kernel(const int* __restrict__ counts, const int* __restrict__ s
 // (one chunk of PLAN_CHUNK positions at a time) and writes the set bits back in order.
 constexpr int PLAN_CHUNK = 1 << 18;              // positions per bitmap chunk (32 KB of bits)
 constexpr int PLAN_WORDS = PLAN_CHUNK / 32;
-__global__ void __launch_bounds__(512)
-plan_sort_heavy_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
-                       const int* __restrict__ heavy, const int* __restrict__ heavy_n,
-                       int heavy_cap, const int* __restrict__ pos_u, int* __restrict__ pos,
-                       unsigned char* __restrict__ eflag, long long n) {
+__device__ __forceinline__ void
+plan_sort_heavy(const int* __restrict__ counts, const int* __restrict__ seg_off,
+                const int* __restrict__ heavy, const int* __restrict__ heavy_n,
+                int heavy_cap, const int* __restrict__ pos_u, int* __restrict__ pos,
+                unsigned char* __restrict__ eflag, long long n, int block, int nblocks) {
   __shared__ unsigned bm[PLAN_WORDS];
   __shared__ int wsum[16];
   __shared__ int run_base;
   int H = *heavy_n;
   if (H > heavy_cap) H = heavy_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int h = blockIdx.x; h < H; h += gridDim.x) {
+  for (int h = block; h < H; h += nblocks) {
     const int r = heavy[h];
     const int c = counts[r], off = seg_off[r];
     if (threadIdx.x == 0) run_base = 0;
@@ -443,6 +443,21 @@ plan_sort_heavy_kernel(const int* __restrict__ counts, const int* __restrict__ s
       __syncthreads();
     }
   }
+}
+
+// Both sorts in one launch: the first `hb` blocks take the heavy segments (the longest work,
+// started first), the others the light ones.
+__global__ void __launch_bounds__(512)
+plan_sort_kernel(const int* __restrict__ counts, const int* __restrict__ seg_off,
+                 const int* __restrict__ num_unique, const int* __restrict__ heavy,
+                 const int* __restrict__ heavy_n, int heavy_cap, int heavy_t,
+                 const int* __restrict__ pos_u, int* __restrict__ pos,
+                 unsigned char* __restrict__ eflag, long long n, int hb) {
+  if ((int)blockIdx.x < hb)
+    plan_sort_heavy(counts, seg_off, heavy, heavy_n, heavy_cap, pos_u, pos, eflag, n, blockIdx.x, hb);
+  else
+    plan_sort_light(counts, seg_off, num_unique, pos_u, pos, heavy_t, (long long)blockIdx.x - hb,
+                    (long long)gridDim.x - hb);
 }
 
 // ---- UnsortedSegmentSum ----------------------------------------------------
@@ -1043,6 +1058,7 @@ Plan* plan_new(int64_t max_ids, int heavy_t, int* rc) {
   return p;
 }
 void plan_delete(Plan* p) { delete p; }
+int64_t plan_capacity(const Plan* p) { return p->cap; }
 
 PlanView plan_view(const Plan* p) {
   PlanView v;
@@ -1089,13 +1105,15 @@ int do_plan_build(Plan* p, Workspace* ws, const int64_t* ids, int64_t n, cudaStr
                         nullptr, st, &po));
   const int dev = p->device;
   KV_CUDA(cudaMemsetAsync(p->eflag, 0, (size_t)((n + 3) & ~3LL), st));  // read four at a time
-  // one warp per 32 distinct ids; U <= n
-  plan_sort_light_kernel<<<blocks_for((n + 31) / 32 * 32, 256, dev, 8), 256, 0, st>>>(
-      p->counts, p->seg_off, p->num, p->pos_u, p->pos, p->heavy_t);
-  KV_LAUNCHED();
-  int hb = p->heavy_cap < 2 * sm_count(dev) ? p->heavy_cap : 2 * sm_count(dev);
-  plan_sort_heavy_kernel<<<hb, 512, 0, st>>>(p->counts, p->seg_off, p->heavy, p->heavy_n,
-                                             p->heavy_cap, p->pos_u, p->pos, p->eflag, n);
+  // heavy segments: a block each; light segments: one warp per 32 distinct ids (U <= n)
+  const int sms = sm_count(dev);
+  int hb = p->heavy_cap < sms ? p->heavy_cap : sms;
+  long long lb = ((n + 31) / 32 * 32 + 511) / 512;
+  if (lb > 3LL * sms) lb = 3LL * sms;
+  if (lb < 1) lb = 1;
+  plan_sort_kernel<<<(unsigned)(hb + lb), 512, 0, st>>>(p->counts, p->seg_off, p->num, p->heavy,
+                                                       p->heavy_n, p->heavy_cap, p->heavy_t, p->pos_u,
+                                                       p->pos, p->eflag, n, hb);
   KV_LAUNCHED();
   return 0;
 }

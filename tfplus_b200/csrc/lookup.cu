@@ -14,6 +14,14 @@
 
 namespace kvhbm {
 
+// dedup.cu: the plan machinery the duplicate-safe scatter borrows
+Plan* plan_new(int64_t max_ids, int heavy_t, int* rc);
+void plan_delete(Plan* p);
+int64_t plan_capacity(const Plan* p);
+PlanView plan_view(const Plan* p);
+int do_plan_build(Plan* p, Workspace* ws, const int64_t* ids, int64_t n, cudaStream_t st);
+Workspace* workspace_new();
+
 // Optional per-warp timeline for kernel tuning (scripts/trace_gather.py): when set, every
 // gather warp records {start ns, end ns, SM id, unused}.
 __device__ unsigned long long* g_trace = nullptr;
@@ -453,10 +461,19 @@ __device__ __forceinline__ float cwise(float l, float r) {
   }
 }
 
-template <int VEC, int CPL, int OP>
+// PLANNED: `ids` are the DISTINCT ids of a dedup plan and every id applies ALL its occurrences
+// upd[pos[seg_off[i] + k]], k = 0 .. counts[i]-1, one after the other in increasing position -
+// ScatterUpdate over raw indices with duplicates (what GradientDescentOptimizer.
+// _resource_apply_sparse_duplicate_indices feeds scatter_add), in the order a sequential walk
+// of the indices applies them.  Otherwise the ids must be distinct (one update row each).
+template <int VEC, int CPL, int OP, bool PLANNED>
 __global__ void __launch_bounds__(256)
 scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __restrict__ upd,
-               long long n, int tpr) {
+               long long n_in, int tpr, const int* __restrict__ d_n,
+               const int* __restrict__ counts, const int* __restrict__ seg_off,
+               const int* __restrict__ plist) {
+  long long n = n_in;
+  if (PLANNED) { const long long dn = *d_n; if (dn < n) n = dn; }
   const int lane = threadIdx.x & 31;
   const long long wpb = blockDim.x >> 5;
   const long long warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -475,7 +492,9 @@ scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __re
     float* row = nullptr;
     long long pos = -1;
     uint32_t ctl = 0;
-    if (valid) {
+    int cnt = 1, off0 = 0;
+    if (valid && PLANNED) { cnt = counts[i]; off0 = seg_off[i]; }
+    if (valid && key != KEY_PAD) {
       Slot s;
       bool claimed;
       pos = find_or_claim(t, key, &s, &claimed);
@@ -486,7 +505,12 @@ scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __re
           row = row_ptr(t, ctl);
         } else {
           ctl = s.ctl;
-          if (ctl & CTL_BLACK) mode = M_SKIP;  // :690 blacklisted keys are skipped
+          // a row pointer is only ever derived from a PUBLISHED ctl: with distinct ids a
+          // found key is always published; should a caller break that contract, wait for
+          // the claimer of this launch instead of touching row 0
+          for (int spin = 0; !(ctl & CTL_READY) && spin < (1 << 22); ++spin)
+            ctl = ld_acquire_u32(&t.slots[pos].ctl);
+          if (!(ctl & CTL_READY) || (ctl & CTL_BLACK)) mode = M_SKIP;  // :690 blacklisted keys are skipped
           else { mode = M_COPY; row = row_ptr(t, ctl); }
         }
       }
@@ -498,22 +522,40 @@ scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __re
       float* rp = shfl_ptr(row, kl);
       const long long k = shfl_ll(key, kl);
       bool big = false;
+      const int c_k = PLANNED ? __shfl_sync(FULL, cnt, kl) : 1;
+      const int o_k = PLANNED ? __shfl_sync(FULL, off0, kl) : 0;
       if (m >= M_COPY) {
         long long r1 = -1, r2 = -1;
         if (m == M_CLAIM) init_rows_of(t, k, &r1, &r2);
-        const float* up = upd + (base + kl) * (long long)dim;
+        Chunk<VEC> cur[CPL];
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
           const int off = (q * tpr + tl) * VEC;
           if (off < dim) {
-            Chunk<VEC> cur, u;
-            if (m == M_CLAIM) init_chunk<VEC>(t, r1, r2, off, cur);
-            else cur.load_cg(rp + off);
-            u.load_stream(up + off);
+            if (m == M_CLAIM) init_chunk<VEC>(t, r1, r2, off, cur[q]);
+            else cur[q].load_cg(rp + off);
+          }
+        }
+        for (int occ = 0; occ < c_k; ++occ) {
+          const long long urow = PLANNED ? (long long)__ldg(plist + o_k + occ) : base + kl;
+          const float* up = upd + urow * (long long)dim;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) cur.v[e] = cwise<OP>(cur.v[e], u.v[e]);
-            cur.store(rp + off);
-            big |= chunk_over_cutoff(cur, DEFAULT_CUTOFF);
+          for (int q = 0; q < CPL; ++q) {
+            const int off = (q * tpr + tl) * VEC;
+            if (off < dim) {
+              Chunk<VEC> u;
+              u.load_stream(up + off);
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) cur[q].v[e] = cwise<OP>(cur[q].v[e], u.v[e]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int off = (q * tpr + tl) * VEC;
+          if (off < dim) {
+            cur[q].store(rp + off);
+            big |= chunk_over_cutoff(cur[q], DEFAULT_CUTOFF);
           }
         }
       }
@@ -786,20 +828,22 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
 
 template <int VEC, int CPL>
 int launch_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t n,
-                   cudaStream_t st, int tpr) {
+                   cudaStream_t st, int tpr, const PlanView* pv) {
   const int blocks = blocks_for(n, 256, tb->device);
-  const long long* k = reinterpret_cast<const long long*>(ids);
+  const long long* k = reinterpret_cast<const long long*>(pv ? pv->uniq : reinterpret_cast<const long long*>(ids));
   TableView v = tb->view();
+#define KV_S(OP)                                                                                   \
+  case OP:                                                                                         \
+    if (pv) scatter_kernel<VEC, CPL, OP, true><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr, pv->num,     \
+                                                                    pv->counts, pv->seg_off, pv->pos); \
+    else scatter_kernel<VEC, CPL, OP, false><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr, nullptr,        \
+                                                                    nullptr, nullptr, nullptr);     \
+    break;
   switch (op) {
-    case 0: scatter_kernel<VEC, CPL, 0><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 1: scatter_kernel<VEC, CPL, 1><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 2: scatter_kernel<VEC, CPL, 2><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 3: scatter_kernel<VEC, CPL, 3><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 4: scatter_kernel<VEC, CPL, 4><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 5: scatter_kernel<VEC, CPL, 5><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
-    case 6: scatter_kernel<VEC, CPL, 6><<<blocks, 256, 0, st>>>(v, k, upd, n, tpr); break;
+    KV_S(0) KV_S(1) KV_S(2) KV_S(3) KV_S(4) KV_S(5) KV_S(6)
     default: return fail(1, "KvVariable: unsupported scatter update operation");
   }
+#undef KV_S
   KV_LAUNCHED();
   return 0;
 }
@@ -983,12 +1027,37 @@ int do_gather_segments(Table* tb, const int64_t* ids, const int32_t* counts, int
 #undef CALL
 }
 
+// unique_ids: the caller guarantees distinct ids (TF's _deduplicate_indexed_slices ran before
+// the op: the tfplus-Adam path).  Otherwise duplicates are applied one after the other in
+// index order, through a dedup plan of the ids kept with the table.
 int do_scatter(Table* tb, int op, const int64_t* ids, const float* upd, int64_t n,
-               cudaStream_t st) {
+               cudaStream_t st, bool unique_ids) {
   if (n <= 0) return 0;
   KV_TRY(tb->ensure(n, st));
   RowGeom g = row_geom(tb->dim);
-#define CALL(V, C) launch_scatter<V, C>(tb, op, ids, upd, n, st, g.tpr)
+  PlanView pv;
+  const PlanView* pvp = nullptr;
+  if (!unique_ids && n > 1) {
+    if (tb->scatter_plan == nullptr || plan_capacity(tb->scatter_plan) < n) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+      if (cs != cudaStreamCaptureStatusNone)
+        return fail(2, "scatter: the duplicate-safe path sizes its dedup plan on first use; run "
+                       "the call once outside CUDA-graph capture");
+      KV_CUDA(cudaStreamSynchronize(st));
+      if (tb->scatter_plan) plan_delete(tb->scatter_plan);
+      int rc = 0;
+      int64_t cap = 1024;
+      while (cap < n) cap <<= 1;
+      tb->scatter_plan = plan_new(cap, 0, &rc);
+      if (rc) return rc;
+      if (tb->scatter_ws == nullptr) tb->scatter_ws = workspace_new();
+    }
+    KV_TRY(do_plan_build(tb->scatter_plan, tb->scatter_ws, ids, n, st));
+    pv = plan_view(tb->scatter_plan);
+    pvp = &pv;
+  }
+#define CALL(V, C) launch_scatter<V, C>(tb, op, ids, upd, n, st, g.tpr, pvp)
   KV_DISPATCH_GEOM(g, CALL);
 #undef CALL
 }

@@ -231,8 +231,13 @@ static uint64_t pow2_at_least(uint64_t x) {
   return p;
 }
 
+void plan_delete(Plan*);
+void workspace_delete(Workspace*);
+
 Table::~Table() {
   cudaSetDevice(device);
+  if (scatter_plan) plan_delete(scatter_plan);
+  if (scatter_ws) workspace_delete(scatter_ws);
   if (d_slots) cudaFree(d_slots);
   if (d_init) cudaFree(d_init);
   if (d_ctr) cudaFree(d_ctr);

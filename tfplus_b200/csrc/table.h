@@ -14,6 +14,10 @@
 
 namespace kvhbm {
 
+struct Plan;
+struct Workspace;
+
+
 // Error plumbing shared by every translation unit.
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
@@ -82,6 +86,9 @@ struct Table {
   uint64_t used_ub = 0;
   uint64_t rows_ub = 0;
   bool captured = false;  // some call on this table was recorded into a CUDA graph
+  // dedup plan + scratch of the duplicate-safe scatter (lookup.cu do_scatter), sized on first use
+  Plan* scatter_plan = nullptr;
+  Workspace* scatter_ws = nullptr;
 
   std::mutex mu;
 

@@ -7,6 +7,7 @@ Method names and meanings follow the reference: sparse_read[_with_counts], scatt
 delete, delete_with_timestamp, total_count, total_freq, is_initialized.
 """
 import threading
+import zlib
 
 import torch
 
@@ -43,7 +44,7 @@ class KvVariable:
     self.kv_options = kv_options
     self.device = torch.device(device if device is not None else "cuda")
     if seed is None:
-      seed = abs(hash(name)) % (2 ** 31) + 1
+      seed = zlib.crc32(name.encode()) % (2 ** 31) + 1   # stable across processes and ranks
     self._handle = ops.kv_variable(key_dtype=key_dtype, value_dtype=value_dtype,
                                    value_shape=[self.embedding_dim],
                                    enter_threshold=enter_threshold, device=self.device,

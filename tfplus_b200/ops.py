@@ -301,7 +301,9 @@ def kv_variable_increase_count_v2(table_handle, indices, counts):
 _SCATTER = {"update": 0, "add": 1, "sub": 2, "mul": 3, "div": 4, "min": 5, "max": 6}
 
 
-def _scatter(op, table_handle, indices, updates):
+def _scatter(op, table_handle, indices, updates, unique_indices=False):
+  """indices may repeat (every occurrence is applied, in index order) unless the caller
+  vouches for distinct ids with unique_indices=True (skips the internal dedup pass)."""
   h = table_handle
   ids = _ids(indices, h)
   upd = _vals(updates, h, "updates")
@@ -309,36 +311,36 @@ def _scatter(op, table_handle, indices, updates):
     return
   if upd.numel() != ids.numel() * h.dim:
     raise ValueError("InvalidArgument: updates must be [%d, %d]" % (ids.numel(), h.dim))
-  check(h._lib.kv_scatter(h._live(), _SCATTER[op], ids.data_ptr(), upd.data_ptr(), ids.numel(),
-                          h.stream))
+  fn = h._lib.kv_scatter_unique if unique_indices else h._lib.kv_scatter
+  check(fn(h._live(), _SCATTER[op], ids.data_ptr(), upd.data_ptr(), ids.numel(), h.stream))
 
 
-def kv_variable_scatter_add_v2(table_handle, indices, updates):
-  _scatter("add", table_handle, indices, updates)
+def kv_variable_scatter_add_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("add", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_sub_v2(table_handle, indices, updates):
-  _scatter("sub", table_handle, indices, updates)
+def kv_variable_scatter_sub_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("sub", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_mul_v2(table_handle, indices, updates):
-  _scatter("mul", table_handle, indices, updates)
+def kv_variable_scatter_mul_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("mul", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_div_v2(table_handle, indices, updates):
-  _scatter("div", table_handle, indices, updates)
+def kv_variable_scatter_div_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("div", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_min_v2(table_handle, indices, updates):
-  _scatter("min", table_handle, indices, updates)
+def kv_variable_scatter_min_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("min", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_max_v2(table_handle, indices, updates):
-  _scatter("max", table_handle, indices, updates)
+def kv_variable_scatter_max_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("max", table_handle, indices, updates, unique_indices)
 
 
-def kv_variable_scatter_update_v2(table_handle, indices, updates):
-  _scatter("update", table_handle, indices, updates)
+def kv_variable_scatter_update_v2(table_handle, indices, updates, unique_indices=False):
+  _scatter("update", table_handle, indices, updates, unique_indices)
 
 
 def kv_variable_get_count_v2(table_handle, indices):

@@ -9,6 +9,8 @@ the unique ids.  Slot variables are KvVariables themselves, created like
 variable_scope.py:1027-1093 does (a slot of a KvVariable is a KvVariable of dim
 D * num_concat_opt_vars with a constant initializer).
 """
+import zlib
+
 import torch
 
 from .. import ops
@@ -28,7 +30,7 @@ class _Optimizer:
       self._slots[key] = KvVariable("%s/%s/%s" % (var.name, self._name, slot_name),
                                     var.embedding_dim * width, initializer=float(value),
                                     device=var.device, init_rows=16,
-                                    seed=abs(hash(key)) % (2 ** 31) + 1)
+                                    seed=zlib.crc32(str(key).encode()) % (2 ** 31) + 1)
     return self._slots[key]
 
   def get_slot(self, var, name):
