@@ -330,6 +330,40 @@ int kv_import(kv_table* t, const int64_t* d_keys, const float* d_values, int64_t
 
 /* ---- eviction ------------------------------------------------------------ */
 
+/* ---- delta checkpoints (online learning) -----------------------------------
+ * KvVariableFullOrDeltaExport / KvVariableFullOrDeltaImport[V2] in delta mode
+ * (ops/kv_variable_ops.cc:576-660; python/ops/kv_variable_ops.py:1435-1459,1609-1621) ->
+ * KvVariable::DeltaExport kernels/dynamic_save.hpp:197-449 and KvVariable::DeltaImport
+ * kernels/dynamic_restore.hpp:28-153.  The reference switches delta tracking on with the
+ * environment variables SUPPORT_DELTA_EXPORT / SUPPORT_PREDICTION_DELTA_EXPORT at construction
+ * (kernels/kv_variable.h:101-111); here it is a call.  From then on every entry point that the
+ * reference marks - GatherOrInsert (:316), InsertOrUpdate (:451), ScatterUpdate (:685), Delete
+ * (:747), DeleteWithTimestamp (:772) and the apply ops through MarkAsDeltaListElements
+ * (:791-799, for the ids they do not skip) - records its keys in a device-side key set. */
+int kv_enable_delta_export(kv_table* t, int support_prediction_delta);
+/* Keys marked since the last training-mode delta export (train_deltalist_.size()). */
+int kv_delta_size(kv_table* t, kv_stream stream, int64_t* out);
+/* Sizes of the four variable-length outputs of a delta export with attr first_n (nothing is
+ * consumed): update rows, blacklist, frequency table (first_n > 4), delete_keys. */
+int kv_delta_export_count(kv_table* t, int first_n, kv_stream stream, int64_t* n_keys,
+                          int64_t* n_blacklist, int64_t* n_freq, int64_t* n_delete);
+/* The export proper into caller buffers of the given capacities (entries beyond a capacity
+ * are dropped, never written); counts[4] = what the table held.  freq_values are full uint32
+ * words (lo16 count, hi16 day).  first_n <= 3 is the inference-mode export (train + prediction
+ * sets, blacklisted keys become delete_keys, prediction set cleared); otherwise the train set
+ * is moved to the prediction set (if enabled) and cleared. */
+int kv_delta_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_t cap_keys,
+                    int64_t* d_blacklist, int64_t cap_blacklist, int64_t* d_freq_keys,
+                    uint32_t* d_freq_values, int64_t cap_freq, int64_t* d_delete_keys,
+                    int64_t cap_delete, kv_stream stream, int64_t* counts);
+/* DeltaImport on top of the current contents: upsert rows (un-blacklisting them), mark /
+ * (first_n <= 3) drop the blacklist keys, overwrite the frequency words of keys that exist,
+ * delete delete_keys. */
+int kv_delta_import(kv_table* t, int first_n, const int64_t* d_keys, const float* d_values,
+                    int64_t n, const int64_t* d_blacklist, int64_t n_blacklist,
+                    const int64_t* d_freq_keys, const uint32_t* d_freq_values, int64_t n_freq,
+                    const int64_t* d_delete_keys, int64_t n_delete, kv_stream stream);
+
 /* KvVariable::Delete, kernels/kv_variable.h:737-753. */
 int kv_delete(kv_table* t, const int64_t* d_ids, int64_t n, kv_stream stream);
 /* KvVariable::DeleteWithTimestamp, kernels/kv_variable.h:756-789: deletes keys

@@ -59,6 +59,11 @@ def lib():
       "kvo_apply_adagrad": (None, [vp, vp, P, P, i64, f32, C.c_int, u16]),
       "kvo_apply_group_adam_v4": (None, [vp, vp, P, P, i64] + [f32] * 9 + [u16]),
       "kvo_apply_sparse_group_ftrl": (None, [vp, vp, vp, P, P, i64] + [f32] * 6 + [u16]),
+      "kvo_enable_delta_export": (None, [vp, C.c_int]),
+      "kvo_delta_size": (i64, [vp]),
+      "kvo_delta_export": (None, [vp, C.c_int, P, P, P, P]),
+      "kvo_delta_export_fetch_deleted": (None, [vp, P]),
+      "kvo_delta_import": (None, [vp, C.c_int, P, P, i64, P, i64, P, P, i64, P, i64]),
       "kvo_apply_group_adam_v3": (None, [vp, vp, P, P, i64] + [f32] * 9 + [u16]),
       "kvo_apply_sparse_ftrl_v2": (None, [vp, vp, vp, P, P, i64] + [f32] * 5 + [u16]),
       "kvo_apply_group_sparse_ftrl_v2": (None, [vp, vp, vp, P, P, i64] + [f32] * 5 + [u16]),
@@ -195,6 +200,39 @@ class OracleTable:
     out = np.empty(ids.size, np.uint32)
     lib().kvo_get_timestamp(self._h, _p(ids), ids.size, _p(out), today)
     return out
+
+  # -- delta checkpoints (dynamic_save.hpp:197-449, dynamic_restore.hpp:28-153) --
+  def enable_delta_export(self, support_prediction_delta=False):
+    lib().kvo_enable_delta_export(self._h, int(bool(support_prediction_delta)))
+
+  def delta_size(self):
+    return int(lib().kvo_delta_size(self._h))
+
+  def delta_export(self, first_n=6):
+    """KvVariableFullOrDeltaExport in delta mode -> dict(keys, values, blacklist, freq_keys,
+    freq_values (uint32 words), delete_keys)."""
+    nk, nb, nf, nd = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    lib().kvo_delta_export(self._h, first_n, C.byref(nk), C.byref(nb), C.byref(nf), C.byref(nd))
+    keys = np.empty(nk.value, np.int64)
+    vals = np.empty((nk.value, self.dim), np.float32)
+    black = np.empty(nb.value, np.int64)
+    fk = np.empty(nf.value, np.int64)
+    fv = np.empty(nf.value, np.uint32)
+    dk = np.empty(nd.value, np.int64)
+    lib().kvo_export_fetch(self._h, _p(keys), _p(vals), _p(black), _p(fk), _p(fv))
+    lib().kvo_delta_export_fetch_deleted(self._h, _p(dk))
+    return dict(keys=keys, values=vals, blacklist=black, freq_keys=fk, freq_values=fv,
+                delete_keys=dk)
+
+  def delta_import(self, keys, values, blacklist, freq_keys, freq_values, delete_keys,
+                   first_n=6):
+    keys = _ids(keys)
+    values = _f32(values).reshape(keys.size, self.dim)
+    blacklist, freq_keys, delete_keys = _ids(blacklist), _ids(freq_keys), _ids(delete_keys)
+    fv = np.ascontiguousarray(freq_values, np.uint32)
+    lib().kvo_delta_import(self._h, first_n, _p(keys), _p(values), keys.size, _p(blacklist),
+                           blacklist.size, _p(freq_keys), _p(fv), freq_keys.size,
+                           _p(delete_keys), delete_keys.size)
 
   def freq_word(self, key):
     return int(lib().kvo_freq_word(self._h, int(key)))

@@ -58,6 +58,7 @@
 #include <mutex>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace {
@@ -347,6 +348,19 @@ struct Table {
   std::vector<float> zero_row;  // TableManager::zero_val_, table_manager.h:63-67
   Segment* seg;
 
+  // delta export (SUPPORT_DELTA_EXPORT / SUPPORT_PREDICTION_DELTA_EXPORT, kv_variable.h:101-111):
+  // keys touched since the last delta export (train_deltalist_, :870) and keys handed to
+  // the prediction side by training-mode exports (prediction_deltalist_, :871)
+  bool support_delta = false, support_pred_delta = false;
+  std::mutex delta_mu;
+  std::unordered_set<int64_t> train_delta, pred_delta;
+  void MarkDelta(int64_t key) {   // `if (NeedDeltaInfo()) train_deltalist_.insert(key)`
+    if (!support_delta) return;
+    std::lock_guard<std::mutex> g(delta_mu);
+    train_delta.insert(key);
+  }
+  std::vector<int64_t> ex_delete;   // delete_keys of the last delta export
+
   // last export, fetched by kvo_export_fetch
   std::vector<int64_t> ex_keys, ex_black, ex_fkeys;
   std::vector<float> ex_vals;
@@ -531,6 +545,7 @@ void kvo_gather_or_insert(void* h, const int64_t* ids, const int32_t* counts,
     for (int64_t i = s; i < e; ++i) {
       const int64_t key = ids[i];
       float* dst = out + i * D;
+      t->MarkDelta(key);   // kv_variable.h:316-318
       const uint16_t f = counts ? SaturateMaxFrequency(counts[i]) : uint16_t(1);
       Segment& sg = t->SegOf(key);
       // read lock first, as the reference does; upgrade on miss.
@@ -597,6 +612,7 @@ void kvo_insert_or_update(void* h, const int64_t* ids, const float* values,
   Pool::Get().ParallelFor(n, 5000, [&](int64_t s, int64_t e) {
     for (int64_t i = s; i < e; ++i) {
       const int64_t key = ids[i];
+      t->MarkDelta(key);   // kv_variable.h:451-453, before the filter test
       if (filter_out && filter_out[i]) continue;
       Segment& sg = t->SegOf(key);
       sg.mu.lock();
@@ -643,6 +659,7 @@ void kvo_scatter(void* h, int op, const int64_t* ids, const float* upd, int64_t 
   Pool::Get().ParallelFor(n, 5000, [&](int64_t s, int64_t e) {
     for (int64_t i = s; i < e; ++i) {
       const int64_t key = ids[i];
+      t->MarkDelta(key);   // kv_variable.h:685-687
       Segment& sg = t->SegOf(key);
       sg.mu.lock();
       EmbeddingValue* ev = t->FindUnsafe(sg, key);
@@ -680,7 +697,9 @@ void kvo_apply_adagrad(void* hvar, void* hacc, const int64_t* ids,
       EmbeddingValue *ev, *ea;
       float* v = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      acc->MarkDelta(key);
       const float* g = grad + i * D;
       if (update_slots)
         for (int j = 0; j < D; ++j) a[j] += g[j] * g[j];
@@ -760,7 +779,9 @@ void kvo_apply_group_adam_v4(void* hvar, void* hmvl, const int64_t* ids,
       EmbeddingValue *ev, *es;
       float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* o = mvl->FindOrInsertUnsafe(key, nullptr, today, &es);
+      mvl->MarkDelta(key);
       float* m = o;
       float* v = o + D;
       float* lin = o + 2 * D;
@@ -822,8 +843,11 @@ void kvo_apply_sparse_group_ftrl(void* hvar, void* hacc, void* hlin,
       EmbeddingValue *ev, *el, *ea;
       float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
       float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      lint->MarkDelta(key);
+      acc->MarkDelta(key);
       const float* g = grad + i * D;
       for (int j = 0; j < D; ++j) {
         gs[j] = g[j] + (2.0f * l2_shrinkage) * w[j];
@@ -884,7 +908,9 @@ void kvo_apply_group_adam_v3(void* hvar, void* hmvl, const int64_t* ids,
       EmbeddingValue *ev, *es;
       float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* o = mvl->FindOrInsertUnsafe(key, nullptr, today, &es);
+      mvl->MarkDelta(key);
       float* m = o;
       float* v = o + D;
       float* lin = o + 2 * D;
@@ -943,8 +969,11 @@ void kvo_apply_sparse_ftrl_v2(void* hvar, void* hacc, void* hlin, const int64_t*
       EmbeddingValue *ev, *el, *ea;
       float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
       float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      lint->MarkDelta(key);
+      acc->MarkDelta(key);
       const float* g = grad + i * D;
       for (int j = 0; j < D; ++j) {
         // every statement of COMPUTE_FTRL is elementwise, so the lazy expressions can be
@@ -989,8 +1018,11 @@ void kvo_apply_group_sparse_ftrl_v2(void* hvar, void* hacc, void* hlin, const in
       EmbeddingValue *ev, *el, *ea;
       float* w = var->FindOrInsertUnsafe(key, &filt, today, &ev);
       if (filt) { sg.mu.unlock(); continue; }
+      var->MarkDelta(key);   // MarkAsDeltaListElements(non-filtered indices), kv_variable.h:791-799
       float* lin = lint->FindOrInsertUnsafe(key, nullptr, today, &el);
       float* a = acc->FindOrInsertUnsafe(key, nullptr, today, &ea);
+      lint->MarkDelta(key);
+      acc->MarkDelta(key);
       const float* g = grad + i * D;
       for (int j = 0; j < D; ++j) {
         gs[j] = g[j] + (2.0f * l2_shrinkage) * w[j];
@@ -1065,7 +1097,10 @@ int kvo_key_flags(void* h, int64_t key) {
 // KvVariable::Delete, kv_variable.h:737-753; TableManager::DeleteKey :405-416.
 void kvo_delete(void* h, const int64_t* ids, int64_t n) {
   Table* t = static_cast<Table*>(h);
-  for (int64_t i = 0; i < n; ++i) t->SegOf(ids[i]).map.erase(ids[i]);
+  for (int64_t i = 0; i < n; ++i) {
+    t->SegOf(ids[i]).map.erase(ids[i]);
+    t->MarkDelta(ids[i]);   // kv_variable.h:747-749
+  }
 }
 // KvVariable::DeleteWithTimestamp, kv_variable.h:756-789.  Returns the number
 // of deleted keys; writes at most `cap` of them to out.
@@ -1081,7 +1116,7 @@ int64_t kvo_delete_with_timestamp(void* h, int threshold, uint16_t today,
                               static_cast<int>(static_cast<uint16_t>(threshold)))
         del.push_back(kv.first);
     }
-  for (int64_t k : del) t->SegOf(k).map.erase(k);
+  for (int64_t k : del) { t->SegOf(k).map.erase(k); t->MarkDelta(k); }   // :772-774
   for (size_t i = 0; i < del.size() && static_cast<int64_t>(i) < cap; ++i) out[i] = del[i];
   return static_cast<int64_t>(del.size());
 }
@@ -1178,6 +1213,95 @@ void kvo_import(void* h, const int64_t* keys, const float* values, int64_t n,
 // the reference tree): output in first-occurrence order, idx
 // int32.  Call sites: TF Optimizer._deduplicate_indexed_slices reached from
 // python/ops/variable_scope.py:1096-1106, and embedding_ops.py:365-372.
+// SUPPORT_DELTA_EXPORT / SUPPORT_PREDICTION_DELTA_EXPORT (kv_variable.h:101-111).
+void kvo_enable_delta_export(void* h, int support_prediction_delta) {
+  Table* t = static_cast<Table*>(h);
+  t->support_delta = true;
+  t->support_pred_delta = support_prediction_delta != 0;
+}
+int64_t kvo_delta_size(void* h) { return static_cast<int64_t>(static_cast<Table*>(h)->train_delta.size()); }
+
+// KvVariable::DeltaExport, dynamic_save.hpp:197-449 (freq_values are full uint32 words).
+// Results are parked in the table: keys/values/blacklist/freq via kvo_export_fetch,
+// delete_keys via kvo_delta_export_fetch_deleted.
+void kvo_delta_export(void* h, int first_n, int64_t* n_keys, int64_t* n_black, int64_t* n_freq,
+                      int64_t* n_delete) {
+  Table* t = static_cast<Table*>(h);
+  const int D = t->dim;
+  std::unordered_set<int64_t> all_delta(t->train_delta.begin(), t->train_delta.end());
+  if (first_n <= 3)   // inference mode: train + prediction (:222-228)
+    all_delta.insert(t->pred_delta.begin(), t->pred_delta.end());
+  t->ex_keys.clear(); t->ex_vals.clear(); t->ex_black.clear();
+  t->ex_fkeys.clear(); t->ex_fvals.clear(); t->ex_delete.clear();
+  for (int64_t key : all_delta) {
+    EmbeddingValue* ev = t->FindUnsafe(t->SegOf(key), key);
+    if (ev == nullptr) { t->ex_delete.push_back(key); continue; }   // :233-236
+    if (t->HasLowFrequency(ev->freq)) continue;                      // :238-240
+    if (ev->in_black) { t->ex_black.push_back(key); continue; }      // :242-245
+    t->ex_keys.push_back(key);
+    t->ex_vals.insert(t->ex_vals.end(), ev->row, ev->row + D);
+  }
+  if (first_n <= 3) {   // prediction mode: blacklisted keys are deleted downstream (:333-339)
+    t->ex_delete.insert(t->ex_delete.end(), t->ex_black.begin(), t->ex_black.end());
+    t->ex_black.clear();
+  }
+  if (first_n > 4) {    // ExportFrequencyDelta, kv_variable.h:937-952
+    for (int64_t key : all_delta) {
+      EmbeddingValue* ev = t->FindUnsafe(t->SegOf(key), key);
+      t->ex_fkeys.push_back(key);
+      t->ex_fvals.push_back(ev ? ev->freq : 0u);
+    }
+  }
+  if (first_n <= 3) {
+    t->pred_delta.clear();                                           // :434-436
+  } else {
+    if (t->support_pred_delta) t->pred_delta.insert(t->train_delta.begin(), t->train_delta.end());
+    t->train_delta.clear();                                          // :438-443
+  }
+  *n_keys = static_cast<int64_t>(t->ex_keys.size());
+  *n_black = static_cast<int64_t>(t->ex_black.size());
+  *n_freq = static_cast<int64_t>(t->ex_fkeys.size());
+  *n_delete = static_cast<int64_t>(t->ex_delete.size());
+}
+void kvo_delta_export_fetch_deleted(void* h, int64_t* delete_keys) {
+  Table* t = static_cast<Table*>(h);
+  if (delete_keys && !t->ex_delete.empty())
+    std::memcpy(delete_keys, t->ex_delete.data(), t->ex_delete.size() * sizeof(int64_t));
+}
+
+// KvVariable::DeltaImport, dynamic_restore.hpp:28-153 (memory table).
+void kvo_delta_import(void* h, int first_n, const int64_t* keys, const float* values, int64_t n,
+                      const int64_t* blacklist, int64_t n_black, const int64_t* freq_keys,
+                      const uint32_t* freq_values, int64_t n_freq, const int64_t* delete_keys,
+                      int64_t n_delete) {
+  Table* t = static_cast<Table*>(h);
+  const int D = t->dim;
+  for (int64_t i = 0; i < n; ++i) {                                  // stage 1, :60-79
+    Segment& sg = t->SegOf(keys[i]);
+    EmbeddingValue* ev = t->FindUnsafe(sg, keys[i]);
+    if (!ev) {
+      EmbeddingValue nv;  // freq 1
+      sg.map[keys[i]] = std::move(nv);
+      ev = t->FindUnsafe(sg, keys[i]);
+    }
+    if (!ev->row) ev->row = t->NewRow();                             // UpdateValue
+    std::memcpy(ev->row, values + i * D, sizeof(float) * D);
+    ev->in_black = false;                                            // RemoveBlacklist
+    t->UpdateUnderThreshold(ev, ev->row);
+  }
+  for (int64_t i = 0; i < n_black; ++i) {                            // stage 2, :93-111
+    if (first_n > 3) t->MarkBlacklistUnsafe(t->SegOf(blacklist[i]), blacklist[i], nullptr);
+    else t->SegOf(blacklist[i]).map.erase(blacklist[i]);
+  }
+  for (int64_t i = 0; i < n_freq; ++i) {                             // stage 3/4, :113-134
+    EmbeddingValue* ev = t->FindUnsafe(t->SegOf(freq_keys[i]), freq_keys[i]);
+    if (ev) ev->freq = freq_values[i];
+  }
+  for (int64_t i = 0; i < n_delete; ++i)                             // stage 5, :136-143
+    t->SegOf(delete_keys[i]).map.erase(delete_keys[i]);
+  t->initialized = true;                                             // :145-151
+}
+
 int64_t kvo_unique(const int64_t* ids, int64_t n, int64_t* uniq, int32_t* idx,
                    int32_t* counts) {
   std::unordered_map<int64_t, int32_t> pos;

@@ -339,6 +339,41 @@ def test_tfplus_adam_equals_dense_adam():
   np.testing.assert_array_equal(mv.gather_or_zeros(ids), np.concatenate([m, v], 1))
 
 
+# --- delta checkpoints (dynamic_save.hpp:197-449, dynamic_restore.hpp:28-153) ---
+def test_delta_export_classes_and_list_handling():
+  dim = 4
+  tb = ob.OracleTable(dim, 2, seed=3)          # enter_threshold 2
+  tb.set_init_table(np.ones((R, dim), np.float32))
+  tb.enable_delta_export(support_prediction_delta=True)
+  tb.gather_or_insert(np.array([1, 2, 2, 3, 3], np.int64))        # 1 stays low-frequency
+  tb.insert_or_update(np.array([3], np.int64), np.zeros((1, dim), np.float32),
+                      blacklist=np.array([1], np.uint8))          # 3 blacklisted
+  tb.delete(np.array([9], np.int64))                              # absent -> delete_keys
+  assert tb.delta_size() == 4
+  d = tb.delta_export(first_n=6)
+  assert d["keys"].tolist() == [2] and np.array_equal(d["values"], np.ones((1, dim), np.float32))
+  assert d["blacklist"].tolist() == [3] and d["delete_keys"].tolist() == [9]
+  assert sorted(d["freq_keys"].tolist()) == [1, 2, 3, 9]           # all_delta, 0 for the absent key
+  fw = dict(zip(d["freq_keys"].tolist(), d["freq_values"].tolist()))
+  assert fw[9] == 0 and (fw[2] & 0xffff) == 2 and (fw[1] & 0xffff) == 1
+  assert tb.delta_size() == 0
+  # training-mode export handed its keys to the prediction list: the inference-mode export
+  # sees them once, with blacklisted keys turned into deletions (:333-339), and clears the list
+  p = tb.delta_export(first_n=3)
+  assert p["keys"].tolist() == [2] and p["blacklist"].size == 0
+  assert sorted(p["delete_keys"].tolist()) == [3, 9] and p["freq_keys"].size == 0
+  assert tb.delta_export(first_n=3)["keys"].size == 0
+  # import on a replica
+  rep = ob.OracleTable(dim, 2, seed=3)
+  rep.set_init_table(np.ones((R, dim), np.float32))
+  rep.gather_or_insert(np.array([2, 9], np.int64))
+  rep.delta_import(d["keys"], d["values"], d["blacklist"], d["freq_keys"], d["freq_values"],
+                   d["delete_keys"], first_n=6)
+  assert rep.map_size() == 2                                       # 2 and the row-less 3; 9 deleted
+  assert rep.freq_word(2) == fw[2]
+  assert np.array_equal(rep.gather_or_zeros(np.array([3, 9])), np.zeros((2, dim), np.float32))
+
+
 # --- TF dedup semantics (TensorFlow 2.13 Unique / UnsortedSegmentSum) ----------
 def test_unique_first_occurrence_order():
   ids = np.array([7, 3, 7, 9, 3, 3, -1, 9], np.int64)

@@ -73,6 +73,12 @@ SIGNATURES = {
     "kv_export": [vp, i32, vp, vp, vp, vp, vp, i32, vp],
     "kv_import": [vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, vp],
     "kv_delete": [vp, vp, i64, vp],
+    "kv_enable_delta_export": [vp, i32],
+    "kv_delta_size": [vp, vp, C.POINTER(i64)],
+    "kv_delta_export_count": [vp, i32, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                              C.POINTER(i64)],
+    "kv_delta_export": [vp, i32, vp, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, C.POINTER(i64)],
+    "kv_delta_import": [vp, i32, vp, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp],
     "kv_delete_with_timestamp": [vp, i32, u16, vp, i64, vp, C.POINTER(i64)],
     "kv_partition_ids": [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp],
     "kv_route_ids": [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],

@@ -77,7 +77,17 @@ int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cud
 int do_import(Table*, const int64_t*, const float*, int64_t, const float*, int64_t, const int64_t*,
               int64_t, const int64_t*, const void*, int64_t, int, cudaStream_t);
 int do_delete(Table*, const int64_t*, int64_t, cudaStream_t);
-int do_delete_older(Table*, int, uint16_t, int64_t*, int64_t, cudaStream_t, int64_t*);
+int do_delete_older(Table*, int, uint16_t, int64_t*, int64_t, cudaStream_t, int64_t*, Table* delta_set);
+int do_delta_mark(Table* set, const int64_t* ids, int64_t n, const int32_t* d_n, Table* main,
+                  bool filter, cudaStream_t st);
+int do_delta_export(Table* tb, Table* train, Table* pred, bool support_pred, int first_n, int write,
+                    int64_t* keys, float* values, int64_t* blacklist, int64_t* freq_keys,
+                    uint32_t* freq_values, int64_t* delete_keys, int64_t cap_k, int64_t cap_b,
+                    int64_t cap_f, int64_t cap_d, cudaStream_t st, int64_t* counts);
+int do_delta_import(Table* tb, int first_n, const int64_t* keys, const float* values, int64_t n,
+                    const int64_t* blacklist, int64_t n_black, const int64_t* freq_keys,
+                    const uint32_t* freq_values, int64_t n_freq, const int64_t* delete_keys,
+                    int64_t n_delete, cudaStream_t st);
 
 // InitRandomValues: only the first call takes effect unless `force` (import).
 int do_set_init_table(Table* tb, const float* d_table, int64_t rows, cudaStream_t st, bool force) {
@@ -103,7 +113,15 @@ int do_set_init_table(Table* tb, const float* d_table, int64_t rows, cudaStream_
 
 using namespace kvhbm;
 
-struct kv_table { Table t; };
+struct kv_table {
+  Table t;
+  // SUPPORT_DELTA_EXPORT (kv_variable.h:101-111): key sets of what changed since the last delta
+  // export; null until kv_enable_delta_export
+  Table* delta_train = nullptr;
+  Table* delta_pred = nullptr;
+  bool support_pred_delta = false;
+  ~kv_table() { delete delta_train; delete delta_pred; }
+};
 struct kv_workspace { Workspace* w; };
 struct kv_plan { Plan* p; };
 
@@ -127,6 +145,26 @@ struct Guard {
   if (_g.rc) return _g.rc
 #define KV_NEED(cond, msg) \
   if (!(cond)) return fail(KV_INVALID_ARGUMENT, msg)
+
+// train_deltalist_.insert(key) for the ids of one call (no-op unless delta export is enabled).
+// filter_by: the apply ops leave out the ids they skip (low-frequency keys of the value table).
+inline int delta_mark(kv_table* t, const int64_t* ids, int64_t n, const int32_t* d_n,
+                      kv_table* filter_by, cudaStream_t st) {
+  if (!t || !t->delta_train || n <= 0 || !ids) return 0;
+  return do_delta_mark(t->delta_train, ids, n, d_n, filter_by ? &filter_by->t : &t->t,
+                       filter_by != nullptr, st);
+}
+#define KV_MARK(t, ids, n, d_n, by) KV_TRY(delta_mark(t, ids, n, d_n, by, S(stream)))
+// MarkAsDeltaListElements on the value table and on every slot table of an apply op, for the
+// ids the op does not skip.  Must run BEFORE the apply (a key the apply inserts is not filtered).
+inline int delta_mark_apply(kv_table* var, kv_table* a, kv_table* b, const int64_t* ids, int64_t n,
+                            const int32_t* d_n, bool filters, cudaStream_t st) {
+  kv_table* by = filters ? var : nullptr;
+  KV_TRY(delta_mark(var, ids, n, d_n, by, st));
+  if (a && a->delta_train) KV_TRY(do_delta_mark(a->delta_train, ids, n, d_n, &var->t, filters, st));
+  if (b && b->delta_train) KV_TRY(do_delta_mark(b->delta_train, ids, n, d_n, &var->t, filters, st));
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -209,12 +247,14 @@ int kv_gather_or_insert(kv_table* t, const int64_t* d_ids, const int32_t* d_coun
                         float* d_out, uint16_t today, kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_insert: bad arguments");
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_gather(&t->t, true, d_ids, d_counts, n, d_out, today, S(stream));
 }
 int kv_gather_or_insert_n(kv_table* t, const int64_t* d_ids, const int32_t* d_counts, int64_t n,
                           const int32_t* d_n, float* d_out, uint16_t today, kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_out)), "gather_or_insert_n: bad arguments");
+  KV_MARK(t, d_ids, n, d_n, nullptr);
   return do_gather(&t->t, true, d_ids, d_counts, n, d_out, today, S(stream), d_n);
 }
 int kv_gather_or_zeros(kv_table* t, const int64_t* d_ids, int64_t n, float* d_out,
@@ -228,18 +268,21 @@ int kv_insert_or_update(kv_table* t, const int64_t* d_ids, const float* d_values
                         kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_values)), "insert_or_update: bad arguments");
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_insert(&t->t, d_ids, d_values, n, d_filter_out, d_blacklist, S(stream));
 }
 int kv_scatter(kv_table* t, int op, const int64_t* d_ids, const float* d_updates, int64_t n,
                kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_updates)), "scatter: bad arguments");
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream), false);
 }
 int kv_scatter_unique(kv_table* t, int op, const int64_t* d_ids, const float* d_updates, int64_t n,
                       kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_updates)), "scatter: bad arguments");
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_scatter(&t->t, op, d_ids, d_updates, n, S(stream), true);
 }
 int kv_get_count(kv_table* t, const int64_t* d_ids, int64_t n, int32_t* d_out, kv_stream stream) {
@@ -280,6 +323,7 @@ int kv_apply_adagrad(kv_table* var, kv_table* accum, const int64_t* d_ids, const
                      kv_stream stream) {
   MultiGuard g(var, accum, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, nullptr, d_ids, n, d_n, true, S(stream)));
   const float hp[1] = {lr};
   return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, hp, nullptr, update_slots,
                           today, S(stream));
@@ -291,6 +335,7 @@ int kv_apply_group_adam_v4(kv_table* var, kv_table* mvl, const int64_t* d_ids,
                            kv_stream stream) {
   MultiGuard g(var, mvl, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, mvl, nullptr, d_ids, n, d_n, true, S(stream)));
   const float hp[9] = {lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21};
   return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, hp, nullptr, today,
                                 S(stream));
@@ -302,6 +347,7 @@ int kv_apply_sparse_group_ftrl(kv_table* var, kv_table* accum, kv_table* linear,
                                kv_stream stream) {
   MultiGuard g(var, accum, linear);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, linear, d_ids, n, d_n, true, S(stream)));
   const float hp[6] = {lr, l1, l2, l21, l2_shrinkage, lr_power};
   return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, hp,
                                     nullptr, today, S(stream));
@@ -311,6 +357,7 @@ int kv_apply_adam(kv_table* var, kv_table* m_v, const int64_t* d_ids, const floa
                   float beta1_power, float beta2_power, uint16_t today, kv_stream stream) {
   MultiGuard g(var, m_v, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, m_v, nullptr, d_ids, n, d_n, false, S(stream)));
   const float hp[6] = {lr, beta1, beta2, epsilon, beta1_power, beta2_power};
   return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, hp, nullptr, today, S(stream));
 }
@@ -321,6 +368,7 @@ int kv_apply_adagrad_dev(kv_table* var, kv_table* accum, const int64_t* d_ids,
                          int update_slots, uint16_t today, kv_stream stream) {
   MultiGuard g(var, accum, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, nullptr, d_ids, n, d_n, true, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_adagrad(&var->t, &accum->t, d_ids, d_grad, n, d_n, nullptr, d_hp, update_slots,
                           today, S(stream));
@@ -330,6 +378,7 @@ int kv_apply_group_adam_v4_dev(kv_table* var, kv_table* mvl, const int64_t* d_id
                                const float* d_hp, uint16_t today, kv_stream stream) {
   MultiGuard g(var, mvl, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, mvl, nullptr, d_ids, n, d_n, true, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today,
                                 S(stream));
@@ -339,6 +388,7 @@ int kv_apply_group_adam_v4_dev_advance(kv_table* var, kv_table* mvl, const int64
                                        float* d_hp, uint16_t today, kv_stream stream) {
   MultiGuard g(var, mvl, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, mvl, nullptr, d_ids, n, d_n, true, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_group_adam_v4(&var->t, &mvl->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today,
                                 S(stream), d_hp);
@@ -349,6 +399,7 @@ int kv_apply_sparse_group_ftrl_dev(kv_table* var, kv_table* accum, kv_table* lin
                                    kv_stream stream) {
   MultiGuard g(var, accum, linear);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, linear, d_ids, n, d_n, true, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_sparse_group_ftrl(&var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n,
                                     nullptr, d_hp, today, S(stream));
@@ -358,6 +409,7 @@ int kv_apply_adam_dev(kv_table* var, kv_table* m_v, const int64_t* d_ids, const 
                       kv_stream stream) {
   MultiGuard g(var, m_v, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, m_v, nullptr, d_ids, n, d_n, false, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream));
 }
@@ -367,6 +419,7 @@ int kv_apply_adam_dev_advance(kv_table* var, kv_table* m_v, const int64_t* d_ids
                               uint16_t today, kv_stream stream) {
   MultiGuard g(var, m_v, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, m_v, nullptr, d_ids, n, d_n, false, S(stream)));
   KV_NEED(d_hp != nullptr, "d_hp is null");
   return do_apply_adam(&var->t, &m_v->t, d_ids, d_grad, n, d_n, nullptr, d_hp, today, S(stream),
                        d_hp);
@@ -380,6 +433,7 @@ int kv_apply_group_adam_v3(kv_table* var, kv_table* mvl, const int64_t* d_ids,
                            kv_stream stream) {
   MultiGuard g(var, mvl, nullptr);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, mvl, nullptr, d_ids, n, d_n, true, S(stream)));
   const float hp[9] = {lr, beta1_power, beta2_power, beta1, beta2, epsilon, l1, l2, l21};
   return do_apply(KV_OPT_GROUP_ADAM_V3, &var->t, &mvl->t, nullptr, d_ids, d_grad, n, d_n, hp,
                   nullptr, 1, today, S(stream), nullptr);
@@ -390,6 +444,7 @@ int kv_apply_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* linear,
                             float lr_power, uint16_t today, kv_stream stream) {
   MultiGuard g(var, accum, linear);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, linear, d_ids, n, d_n, true, S(stream)));
   const float hp[6] = {lr, l1, l2, 0.f, l2_shrinkage, lr_power};
   return do_apply(KV_OPT_SPARSE_FTRL_V2, &var->t, &accum->t, &linear->t, d_ids, d_grad, n, d_n, hp,
                   nullptr, 1, today, S(stream), nullptr);
@@ -401,6 +456,7 @@ int kv_apply_group_sparse_ftrl_v2(kv_table* var, kv_table* accum, kv_table* line
                                   kv_stream stream) {
   MultiGuard g(var, accum, linear);
   if (g.rc) return g.rc;
+  KV_TRY(delta_mark_apply(var, accum, linear, d_ids, n, d_n, true, S(stream)));
   const float hp[6] = {lr, l1, l2, 0.f, l2_shrinkage, lr_power};
   return do_apply(KV_OPT_GROUP_SPARSE_FTRL_V2, &var->t, &accum->t, &linear->t, d_ids, d_grad, n,
                   d_n, hp, nullptr, 1, today, S(stream), nullptr);
@@ -452,6 +508,7 @@ int kv_gather_or_insert_plan(kv_table* t, kv_plan* plan, float* d_out, uint16_t 
   KV_ENTER(t);
   KV_NEED(plan && d_out, "gather_or_insert_plan: bad arguments");
   const PlanView v = plan_view(plan->p);
+  KV_MARK(t, reinterpret_cast<const int64_t*>(v.uniq), v.n, v.num, nullptr);
   return do_gather_plan(&t->t, true, v, v.first, d_out, today, S(stream));
 }
 int kv_gather_or_zeros_plan(kv_table* t, kv_plan* plan, float* d_out, kv_stream stream) {
@@ -481,6 +538,11 @@ int kv_apply_plan(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_b, k
   if (g.rc) return g.rc;
   KV_NEED(plan && hp, "apply_plan: bad arguments");
   KV_NEED(n_hp_of(kind) == n_hp, "apply_plan: wrong number of scalar inputs for this optimizer");
+  {
+    const PlanView v = plan_view(plan->p);
+    KV_TRY(delta_mark_apply(var, slot_a, slot_b, reinterpret_cast<const int64_t*>(v.uniq), v.n, v.num,
+                            kind != KV_OPT_ADAM, S(stream)));
+  }
   return do_apply_plan(kind, &var->t, &slot_a->t, slot_b ? &slot_b->t : nullptr, plan->p, d_grad,
                        hp, nullptr, update_slots, today, S(stream), nullptr);
 }
@@ -490,6 +552,11 @@ int kv_apply_plan_dev(int kind, kv_table* var, kv_table* slot_a, kv_table* slot_
   MultiGuard g(var, slot_a, slot_b);
   if (g.rc) return g.rc;
   KV_NEED(plan && d_hp && n_hp_of(kind) > 0, "apply_plan_dev: bad arguments");
+  {
+    const PlanView v = plan_view(plan->p);
+    KV_TRY(delta_mark_apply(var, slot_a, slot_b, reinterpret_cast<const int64_t*>(v.uniq), v.n, v.num,
+                            kind != KV_OPT_ADAM, S(stream)));
+  }
   return do_apply_plan(kind, &var->t, &slot_a->t, slot_b ? &slot_b->t : nullptr, plan->p, d_grad,
                        nullptr, d_hp, update_slots, today, S(stream),
                        advance_powers ? d_hp : nullptr);
@@ -554,14 +621,76 @@ int kv_import(kv_table* t, const int64_t* d_keys, const float* d_values, int64_t
   return do_import(&t->t, d_keys, d_values, n, d_init_table, init_rows, d_blacklist, n_blacklist,
                    d_freq_keys, d_freq_values, n_freq, freq_u32, S(stream));
 }
+int kv_enable_delta_export(kv_table* t, int support_prediction_delta) {
+  KV_ENTER(t);
+  t->support_pred_delta = support_prediction_delta != 0;
+  for (Table** set : {&t->delta_train, &t->delta_pred}) {
+    if (*set) continue;
+    *set = new Table();
+    const int rc = (*set)->create(1, 0, 1024);
+    if (rc) { delete *set; *set = nullptr; return rc; }
+  }
+  return KV_OK;
+}
+int kv_delta_export_count(kv_table* t, int first_n, kv_stream stream, int64_t* n_keys,
+                          int64_t* n_blacklist, int64_t* n_freq, int64_t* n_delete) {
+  KV_ENTER(t);
+  KV_NEED(t->delta_train != nullptr, "delta export is not enabled on this table");
+  int64_t c[4];
+  KV_TRY(do_delta_export(&t->t, t->delta_train, t->delta_pred, t->support_pred_delta, first_n, 0,
+                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, S(stream), c));
+  if (n_keys) *n_keys = c[0];
+  if (n_blacklist) *n_blacklist = c[1];
+  if (n_freq) *n_freq = c[2];
+  if (n_delete) *n_delete = c[3];
+  return KV_OK;
+}
+int kv_delta_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_t cap_keys,
+                    int64_t* d_blacklist, int64_t cap_blacklist, int64_t* d_freq_keys,
+                    uint32_t* d_freq_values, int64_t cap_freq, int64_t* d_delete_keys,
+                    int64_t cap_delete, kv_stream stream, int64_t* counts) {
+  KV_ENTER(t);
+  KV_NEED(t->delta_train != nullptr, "delta export is not enabled on this table");
+  KV_NEED(cap_keys >= 0 && cap_blacklist >= 0 && cap_freq >= 0 && cap_delete >= 0 &&
+              (cap_keys == 0 || (d_keys && d_values)) && (cap_blacklist == 0 || d_blacklist) &&
+              (cap_freq == 0 || (d_freq_keys && d_freq_values)) && (cap_delete == 0 || d_delete_keys),
+          "delta_export: bad arguments");
+  int64_t c[4];
+  KV_TRY(do_delta_export(&t->t, t->delta_train, t->delta_pred, t->support_pred_delta, first_n, 1,
+                         d_keys, d_values, d_blacklist, d_freq_keys, d_freq_values, d_delete_keys,
+                         cap_keys, cap_blacklist, cap_freq, cap_delete, S(stream), c));
+  if (counts) for (int i = 0; i < 4; ++i) counts[i] = c[i];
+  return KV_OK;
+}
+int kv_delta_import(kv_table* t, int first_n, const int64_t* d_keys, const float* d_values,
+                    int64_t n, const int64_t* d_blacklist, int64_t n_blacklist,
+                    const int64_t* d_freq_keys, const uint32_t* d_freq_values, int64_t n_freq,
+                    const int64_t* d_delete_keys, int64_t n_delete, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(n >= 0 && n_blacklist >= 0 && n_freq >= 0 && n_delete >= 0, "delta_import: negative size");
+  KV_NEED((n == 0 || (d_keys && d_values)) && (n_blacklist == 0 || d_blacklist) &&
+              (n_freq == 0 || (d_freq_keys && d_freq_values)) && (n_delete == 0 || d_delete_keys),
+          "delta_import: bad arguments");
+  return do_delta_import(&t->t, first_n, d_keys, d_values, n, d_blacklist, n_blacklist, d_freq_keys,
+                         d_freq_values, n_freq, d_delete_keys, n_delete, S(stream));
+}
+int kv_delta_size(kv_table* t, kv_stream stream, int64_t* out) {
+  KV_ENTER(t);
+  KV_NEED(t->delta_train != nullptr && out, "delta export is not enabled on this table");
+  KV_TRY(t->delta_train->sync_counters(S(stream)));
+  *out = (int64_t)t->delta_train->h_ctr->used;
+  return KV_OK;
+}
 int kv_delete(kv_table* t, const int64_t* d_ids, int64_t n, kv_stream stream) {
   KV_ENTER(t);
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_delete(&t->t, d_ids, n, S(stream));
 }
 int kv_delete_with_timestamp(kv_table* t, int threshold, uint16_t today, int64_t* d_out_keys,
                              int64_t cap, kv_stream stream, int64_t* n_deleted) {
   KV_ENTER(t);
-  return do_delete_older(&t->t, threshold, today, d_out_keys, cap, S(stream), n_deleted);
+  return do_delete_older(&t->t, threshold, today, d_out_keys, cap, S(stream), n_deleted,
+                         t->delta_train);
 }
 
 int kv_partition_ids(kv_workspace* ws, const int64_t* d_ids, int64_t n, const int32_t* d_n,
@@ -626,6 +755,7 @@ int kv_gather_or_insert_peer(kv_table* t, const int64_t* d_ids, const int32_t* d
                              uint16_t today, kv_stream stream) {
   KV_ENTER(t);
   KV_NEED(n >= 0 && (n == 0 || (d_ids && d_seg_rows)), "gather_or_insert_peer: bad arguments");
+  KV_MARK(t, d_ids, n, nullptr, nullptr);
   return do_gather_segments(&t->t, d_ids, d_counts, n, d_seg_rows, capacity, today, S(stream));
 }
 int kv_scatter_rows_n_peer(const float* d_src, const int32_t* d_perm, int64_t n,

@@ -393,6 +393,76 @@ def kv_variable_export(table_handle, first_n=3, enable_cutoff=False, cutoff_valu
   return keys, values, init_table, blacklist, freq_keys, freq_values
 
 
+def kv_variable_enable_delta_export(table_handle, support_prediction_delta=False):
+  """SUPPORT_DELTA_EXPORT / SUPPORT_PREDICTION_DELTA_EXPORT (kernels/kv_variable.h:101-111): from
+  now on the table records which keys change."""
+  h = table_handle
+  check(h._lib.kv_enable_delta_export(h._live(), int(bool(support_prediction_delta))))
+
+
+def kv_variable_delta_size(table_handle):
+  import ctypes as C
+  h = table_handle
+  out = C.c_int64()
+  check(h._lib.kv_delta_size(h._live(), h.stream, C.byref(out)))
+  return out.value
+
+
+def kv_variable_full_or_delta_export(table_handle, first_n=6, do_full_export=False,
+                                     enable_cutoff=False, cutoff_value=0.0):
+  """Op `KvVariableFullOrDeltaExport` (ops/kv_variable_ops.cc:633-660): the 8-tensor format
+  (keys, values, init_table, blacklist, freq_keys, freq_values uint32, need_full_import,
+  delete_keys).  do_full_export routes to the full export (dynamic_save.hpp FullExport),
+  otherwise KvVariable::DeltaExport (:197-449)."""
+  import ctypes as C
+  h = table_handle
+  dev = h.device
+  if do_full_export:
+    k, v, it, bl, fk, fv = kv_variable_export(h, first_n=first_n, enable_cutoff=enable_cutoff,
+                                              cutoff_value=cutoff_value, freq_dtype=torch.int32)
+    return (k, v, it, bl, fk, fv, torch.ones(1, dtype=torch.bool),
+            torch.empty(0, dtype=torch.int64, device=dev))
+  nk, nb, nf, nd = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+  check(h._lib.kv_delta_export_count(h._live(), first_n, h.stream, C.byref(nk), C.byref(nb),
+                                     C.byref(nf), C.byref(nd)))
+  keys = torch.empty(nk.value, dtype=torch.int64, device=dev)
+  values = torch.empty((nk.value, h.dim), dtype=torch.float32, device=dev)
+  blacklist = torch.empty(nb.value, dtype=torch.int64, device=dev)
+  freq_keys = torch.empty(nf.value, dtype=torch.int64, device=dev)
+  freq_values = torch.empty(nf.value, dtype=torch.int32, device=dev)   # uint32 payload
+  delete_keys = torch.empty(nd.value, dtype=torch.int64, device=dev)
+  counts = (C.c_int64 * 4)()
+  check(h._lib.kv_delta_export(h.ptr, first_n, _ptr(keys), _ptr(values), nk.value,
+                               _ptr(blacklist), nb.value, _ptr(freq_keys), _ptr(freq_values),
+                               nf.value, _ptr(delete_keys), nd.value, h.stream, counts))
+  init_table = torch.empty((0, h.dim), dtype=torch.float32, device=dev)   # :312-325: empty
+  return (keys, values, init_table, blacklist, freq_keys, freq_values,
+          torch.zeros(1, dtype=torch.bool), delete_keys)
+
+
+def kv_variable_full_or_delta_import_v2(table_handle, keys, values, init_table, blacklist,
+                                        freq_keys, freq_values, need_full_import, delete_keys,
+                                        first_n=6):
+  """Op `KvVariableFullOrDeltaImportV2` (ops/kv_variable_ops.cc:604-631): need_full_import
+  routes to ImportValues, otherwise KvVariable::DeltaImport (dynamic_restore.hpp:28-153)."""
+  h = table_handle
+  if bool(torch.as_tensor(need_full_import).reshape(-1)[0]):
+    return kv_variable_import(h, keys, values, init_table, blacklist, freq_keys, freq_values,
+                              first_n=first_n)
+  keys = _ids(keys, h)
+  values = _vals(values, h)
+  bl = _ids(blacklist, h)
+  fk = _ids(freq_keys, h)
+  fv = torch.as_tensor(freq_values).to(h.device)
+  if fv.dtype not in (torch.int32, torch.uint32):
+    fv = fv.to(torch.int32)
+  fv = fv.contiguous()
+  dk = _ids(delete_keys, h)
+  check(h._lib.kv_delta_import(h._live(), first_n, _ptr(keys), _ptr(values), keys.numel(),
+                               _ptr(bl), bl.numel(), _ptr(fk), _ptr(fv), fk.numel(), _ptr(dk),
+                               dk.numel(), h.stream))
+
+
 def read_kv_variable_op_v2(table_handle):
   """Op `ReadKvVariableOpV2` = ExportValues(first_n=2) (kv_variable_ops.cc:325-346);
   like the reference it resets every under-threshold flag (enable_cutoff=false)."""
