@@ -696,17 +696,19 @@ class ShardedStepper:
 
   STAGES = ["route+lookup", "grads+apply"]
 
-  def __init__(self, keys_per_gpu, dim, batch, hp, dev, rank, world):
+  def __init__(self, keys_per_gpu, dim, batch, hp, dev, rank, world, slot_mult=3):
     import torch
     from tfplus_b200 import ops, sharded
+    self.optimizer = "group_adam"      # "adam": slot_mult = 2, hpt = Adam's scalar inputs
     self.torch, self.ops, self.sharded = torch, ops, sharded
     self.keys, self.dim, self.batch, self.dev = keys_per_gpu, dim, batch, dev
     self.rank, self.world, self.hp = rank, world, hp
     cap = int(keys_per_gpu * 1.15) + batch
-    self.tbl = sharded.ShardedKvVariable(dim, world, rank, dev, slot_dims=(3 * dim,),
-                                 capacity_hint=cap, seed=1)
+    self.tbl = sharded.ShardedKvVariable(dim, world, rank, dev, slot_dims=(slot_mult * dim,),
+                                         capacity_hint=cap, seed=1)
     self.ops.init_kv_variable_v2(self.tbl.var, torch.from_numpy(init_table(dim)).to(dev))
-    self.ops.init_kv_variable_v2(self.tbl.slots[0], torch.zeros(INIT_ROWS, 3 * dim, device=dev))
+    self.ops.init_kv_variable_v2(self.tbl.slots[0],
+                                 torch.zeros(INIT_ROWS, slot_mult * dim, device=dev))
     self.hpt = torch.tensor([hp["lr"], hp["beta1"], hp["beta2"], hp["beta1"], hp["beta2"],
                              hp["epsilon"], hp["l1"], hp["l2"], hp["l21"]], dtype=torch.float32,
                             device=dev)
@@ -749,8 +751,10 @@ class ShardedStepper:
     from tfplus_b200 import _lib
     t = self.torch
     self.ids_d, self.grads_d = ids_d, grads_d
-    self.padded = self.sharded.make_padded_step(self.tbl.var, self.tbl.slots[0], self.dim, self.batch,
-                                   self.world, self.rank, self.dev, self.hpt, self.betas)
+    self.padded = self.sharded.make_padded_step(self.tbl.var, self.tbl.slots[0], self.dim,
+                                                self.batch, self.world, self.rank, self.dev,
+                                                self.hpt, self.betas)
+    self.padded.optimizer = self.optimizer
     l0 = _lib.launch_count()
     for i in range(2):
       self.step_eager(ids_d[i], grads_d[i])
@@ -1049,9 +1053,18 @@ def main():
   ap.add_argument("--dim", type=int, default=DIM)
   ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
   ap.add_argument("--no-check", action="store_true", help="skip the untimed parity self-check")
+  ap.add_argument("--config", default="microbench",
+                  choices=["microbench", "ncf", "dcn", "sharded200m", "streaming"],
+                  help="BASELINE.json config: microbench = configs[1] (the metric's own, default); "
+                       "the others are measured by bench_configs.py")
   args = ap.parse_args()
   if args.impl == "reference":
     return main_reference(args)
+  if args.config != "microbench":
+    import bench_configs
+    bench_configs.bench._OUT = _OUT      # (this file runs as __main__: share the real stdout)
+    bench_configs.RUNNERS[args.config](args)
+    return 0
   return main_ours(args)
 
 

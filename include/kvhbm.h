@@ -68,6 +68,11 @@ int kv_set_seed(kv_table* t, uint64_t seed);
 /* Make room for `n_keys` more keys now, so that later calls never have to
  * resize (needed before CUDA-graph capture). */
 int kv_reserve(kv_table* t, int64_t n_keys, kv_stream stream);
+/* Under CUDA-graph capture the host books nothing, so replays can insert more keys than
+ * kv_reserve made room for.  The kernels then never touch unmapped memory but raise a sticky
+ * flag; this call (and every call that reads the table's counters: size, export, growth)
+ * returns an error once the flag is set.  Synchronises the stream. */
+int kv_check_overflow(kv_table* t, kv_stream stream);
 /* InitKvVariableOp -> KvVariable::InitRandomValues, kernels/kv_variable.h:184-206:
  * copies d_table[rows, dim]; only the first call takes effect. */
 int kv_set_init_table(kv_table* t, const float* d_table, int64_t rows, kv_stream stream);
@@ -318,6 +323,12 @@ int kv_export_count(kv_table* t, int first_n, int enable_cutoff, float cutoff_va
 int kv_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values,
               int64_t* d_blacklist, int64_t* d_freq_keys, void* d_freq_values,
               int freq_u32, kv_stream stream);
+/* The same with the sizes of the caller's buffers: entries beyond a capacity are dropped instead
+ * of written (the reference's `key_row < num_rows` guards, dynamic_save.hpp:142-174).  Use this
+ * one when another thread may insert between kv_export_count and the export. */
+int kv_export_bounded(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_t cap_keys,
+                      int64_t* d_blacklist, int64_t cap_blacklist, int64_t* d_freq_keys,
+                      void* d_freq_values, int64_t cap_freq, int freq_u32, kv_stream stream);
 /* KvVariable::ImportValues, kernels/dynamic_restore.hpp:156-262: clears the
  * table, copies the rows (the reference aliases the input tensor), replaces
  * the init table if init_rows > 0, marks the blacklist, overwrites frequency

@@ -470,7 +470,7 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
       for (int j = 0; j < 4; ++j) gp4[j] = j < gcnt ? __ldg(gs.pos + goff + j) : 0;
     }
   }
-  if (mine && key != KEY_PAD) {  // padding ids of the shard exchange are skipped
+  if (mine && !key_reserved(key)) {  // padding ids of the shard exchange are skipped
     Probe pv = probe_begin(var, key), pa = probe_begin(sa, key), pb = probe_begin(sb, key);
     int rv = -1, ra = -1, rb = TWO ? -1 : 0;
     Slot sv, ssa, ssb, x0, x1, y0, y1, z0, z1;

@@ -73,7 +73,8 @@ int do_scatter_rows_n(const float*, const int32_t*, int64_t, const int32_t*, int
                       float* const*, int64_t, cudaStream_t);
 int do_stats(Table*, cudaStream_t, int64_t*, int64_t*, int64_t*);
 int do_export_count(Table*, int, int, float, cudaStream_t, int64_t*, int64_t*, int64_t*);
-int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cudaStream_t);
+int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cudaStream_t,
+              int64_t cap_k, int64_t cap_b, int64_t cap_f);
 int do_import(Table*, const int64_t*, const float*, int64_t, const float*, int64_t, const int64_t*,
               int64_t, const int64_t*, const void*, int64_t, int, cudaStream_t);
 int do_delete(Table*, const int64_t*, int64_t, cudaStream_t);
@@ -133,12 +134,16 @@ inline cudaStream_t S(kv_stream s) { return static_cast<cudaStream_t>(s); }
 struct Guard {
   std::unique_lock<std::mutex> l;
   int rc = 0;
+  int prev = -1;   // the caller's current device, put back on return
   explicit Guard(kv_table* t) {
     if (!t) { rc = fail(KV_INVALID_ARGUMENT, "null table handle"); return; }
     l = std::unique_lock<std::mutex>(t->t.mu);
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev == t->t.device) { prev = -1; return; }
     cudaError_t e = cudaSetDevice(t->t.device);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
   }
+  ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 #define KV_ENTER(t)      \
   Guard _g(t);           \
@@ -203,11 +208,20 @@ int kv_set_seed(kv_table* t, uint64_t seed) {
 int kv_reserve(kv_table* t, int64_t n_keys, kv_stream stream) {
   KV_ENTER(t);
   Table& tb = t->t;
+  KV_NEED(n_keys >= 0, "reserve: negative size");
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(S(stream), &cs) != cudaSuccess) cudaGetLastError();
+  KV_NEED(cs == cudaStreamCaptureStatusNone, "reserve: not while the stream is being captured");
   KV_TRY(tb.ensure(n_keys, S(stream), /*exact=*/true));
-  // ensure() books the keys as used; a reservation does not insert anything
+  // ensure() booked the keys as used (it always does outside capture); a reservation does not
+  // insert anything
   tb.used_ub -= (uint64_t)n_keys;
   tb.rows_ub -= (uint64_t)n_keys;
   return KV_OK;
+}
+int kv_check_overflow(kv_table* t, kv_stream stream) {
+  KV_ENTER(t);
+  return t->t.sync_counters(S(stream));
 }
 int kv_set_init_table(kv_table* t, const float* d_table, int64_t rows, kv_stream stream) {
   KV_ENTER(t);
@@ -301,6 +315,8 @@ namespace {
 struct MultiGuard {
   std::unique_lock<std::mutex> l[3];
   int rc = 0;
+  int prev = -1;
+  ~MultiGuard() { if (prev >= 0) cudaSetDevice(prev); }
   MultiGuard(kv_table* a, kv_table* b, kv_table* c) {
     kv_table* v[3] = {a, b, c};
     int k = c ? 3 : 2;
@@ -312,6 +328,8 @@ struct MultiGuard {
         if (v[j] < v[i]) { kv_table* x = v[i]; v[i] = v[j]; v[j] = x; }
       }
     for (int i = 0; i < k; ++i) l[i] = std::unique_lock<std::mutex>(v[i]->t.mu);
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev == a->t.device) { prev = -1; return; }
     cudaError_t e = cudaSetDevice(a->t.device);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
   }
@@ -610,7 +628,15 @@ int kv_export(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_
               int64_t* d_freq_keys, void* d_freq_values, int freq_u32, kv_stream stream) {
   KV_ENTER(t);
   return do_export(&t->t, first_n, d_keys, d_values, d_blacklist, d_freq_keys, d_freq_values,
-                   freq_u32, S(stream));
+                   freq_u32, S(stream), -1, -1, -1);
+}
+int kv_export_bounded(kv_table* t, int first_n, int64_t* d_keys, float* d_values, int64_t cap_keys,
+                      int64_t* d_blacklist, int64_t cap_blacklist, int64_t* d_freq_keys,
+                      void* d_freq_values, int64_t cap_freq, int freq_u32, kv_stream stream) {
+  KV_ENTER(t);
+  KV_NEED(cap_keys >= 0 && cap_blacklist >= 0 && cap_freq >= 0, "export: negative capacity");
+  return do_export(&t->t, first_n, d_keys, d_values, d_blacklist, d_freq_keys, d_freq_values,
+                   freq_u32, S(stream), cap_keys, cap_blacklist, cap_freq);
 }
 int kv_import(kv_table* t, const int64_t* d_keys, const float* d_values, int64_t n,
               const float* d_init_table, int64_t init_rows, const int64_t* d_blacklist,

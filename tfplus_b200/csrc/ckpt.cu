@@ -88,9 +88,13 @@ __global__ void export_count_kernel(TableView t, int first_n) {
 }
 
 // One warp per slot: lane 0 reserves the output positions, the warp copies the row.
+// cap_*: sizes of the caller's buffers (what kv_export_count returned).  The count and the export
+// are two calls; should another thread have inserted in between, entries beyond a capacity are
+// dropped, as the reference's `key_row < num_rows` guards do (dynamic_save.hpp:142-174).
 __global__ void export_kernel(TableView t, int first_n, long long* keys, float* values,
                               long long* blacklist, long long* freq_keys, void* freq_values,
-                              int freq_u32) {
+                              int freq_u32, unsigned long long cap_k, unsigned long long cap_b,
+                              unsigned long long cap_f) {
   const int lane = threadIdx.x & 31;
   unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -100,17 +104,25 @@ __global__ void export_kernel(TableView t, int first_n, long long* keys, float* 
     const int c = export_class(t, s, first_n);
     unsigned long long p = 0;
     if (lane == 0) {
-      if (c == 0 && keys) { p = atomicAdd(&t.ctr->scratch[0], 1ULL); keys[p] = s.key; }
-      if (c == 1 && blacklist) blacklist[atomicAdd(&t.ctr->scratch[1], 1ULL)] = s.key;
+      if (c == 0 && (keys || values)) {
+        p = atomicAdd(&t.ctr->scratch[0], 1ULL);
+        if (keys && p < cap_k) keys[p] = s.key;
+      }
+      if (c == 1 && blacklist) {
+        const unsigned long long q = atomicAdd(&t.ctr->scratch[1], 1ULL);
+        if (q < cap_b) blacklist[q] = s.key;
+      }
       if (freq_keys) {
         const unsigned long long q = atomicAdd(&t.ctr->scratch[2], 1ULL);
-        freq_keys[q] = s.key;
-        if (freq_u32) static_cast<uint32_t*>(freq_values)[q] = freq_to_ref(s.freq);
-        else static_cast<uint16_t*>(freq_values)[q] = (uint16_t)freq_count(s.freq);
+        if (q < cap_f) {
+          freq_keys[q] = s.key;
+          if (freq_u32) static_cast<uint32_t*>(freq_values)[q] = freq_to_ref(s.freq);
+          else static_cast<uint16_t*>(freq_values)[q] = (uint16_t)freq_count(s.freq);
+        }
       }
     }
-    if (c == 0 && values) {
-      p = __shfl_sync(FULL, p, 0);
+    p = __shfl_sync(FULL, p, 0);
+    if (c == 0 && values && p < cap_k) {
       const float* r = row_ptr(t, s.ctl);
       float* o = values + p * (unsigned long long)t.dim;
       for (int j = lane; j < t.dim; j += 32) o[j] = __ldcg(r + j);
@@ -266,7 +278,9 @@ int do_export_count(Table* tb, int first_n, int enable_cutoff, float cutoff, cud
 }
 
 int do_export(Table* tb, int first_n, int64_t* keys, float* values, int64_t* blacklist,
-              int64_t* freq_keys, void* freq_values, int freq_u32, cudaStream_t st) {
+              int64_t* freq_keys, void* freq_values, int freq_u32, cudaStream_t st,
+              int64_t cap_k, int64_t cap_b, int64_t cap_f) {
+  const unsigned long long NOCAP = ~0ULL;
   KV_TRY(zero_scratch(tb, st));
   if (first_n <= 3) blacklist = nullptr;
   if (first_n <= 4) { freq_keys = nullptr; freq_values = nullptr; }
@@ -274,7 +288,8 @@ int do_export(Table* tb, int first_n, int64_t* keys, float* values, int64_t* bla
   export_kernel<<<blocks_for(tb->capacity * 32, 256, tb->device), 256, 0, st>>>(
       tb->view(), first_n, reinterpret_cast<long long*>(keys), values,
       reinterpret_cast<long long*>(blacklist), reinterpret_cast<long long*>(freq_keys),
-      freq_values, freq_u32);
+      freq_values, freq_u32, cap_k < 0 ? NOCAP : (unsigned long long)cap_k,
+      cap_b < 0 ? NOCAP : (unsigned long long)cap_b, cap_f < 0 ? NOCAP : (unsigned long long)cap_f);
   KV_LAUNCHED();
   return 0;
 }
@@ -297,7 +312,7 @@ __global__ void delta_mark_kernel(TableView set, const long long* __restrict__ i
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const long long key = ids[i];
-    if (key == KEY_PAD || key == KEY_EMPTY || key == KEY_TOMB) continue;
+    if (key_reserved(key)) continue;
     if (filter) {
       Slot m;
       if (find_slot(main, key, &m) >= 0 && freq_count(m.freq) < main.enter_threshold) continue;

@@ -25,6 +25,11 @@ constexpr long long KEY_TOMB = (long long)0x8000000000000001ULL;
 // Also the padding id of the fixed-capacity shard exchange: lookups of it return zeros, applies
 // skip it, nothing probes the table for it (kv_route_ids pads its send buffers with it).
 constexpr long long KEY_PAD = KEY_TOMB;
+// The two sentinel values cannot be stored: every kernel treats them as padding (lookups
+// return zeros, updates skip them) instead of letting INT64_MIN match an empty slot.
+__host__ __device__ __forceinline__ bool key_reserved(long long k) {
+  return k == KEY_EMPTY || k == KEY_TOMB;
+}
 
 constexpr uint32_t CTL_READY = 0x80000000u;  // row contents are published
 constexpr uint32_t CTL_BLACK = 0x40000000u;  // EmbeddingValue::in_black_
@@ -46,7 +51,9 @@ struct Counters {
   unsigned long long tombstones;
   unsigned long long scratch[4];  // per-call reduction results (size, sum_freq, export counts)
   unsigned int apply_done;        // blocks of the running apply launch that have finished
-  unsigned int pad_;
+  unsigned int overflow;          // sticky: a kernel ran out of mapped rows (bit 0) or of probe
+                                  // room (bit 1) - only reachable when captured work is replayed
+                                  // past what kv_reserve made room for; reported by the host
 };
 
 // What a kernel needs to know about one table; passed by value.
@@ -63,6 +70,7 @@ struct TableView {
   uint32_t enter_threshold;
   Counters* ctr;
   uint32_t* free_rows;
+  unsigned long long rows_cap;  // rows the arena has mapped: the bump allocator's bound
 };
 
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -184,7 +192,8 @@ __device__ __forceinline__ long long find_or_claim(const TableView& t, long long
       probe_skip(t, &p, pos);
     }
   }
-  return -1;  // table full: the host sizing guarantees this cannot happen
+  atomicOr(&t.ctr->overflow, 2u);
+  return -1;  // table full: only reachable past the host's reservation (see Counters::overflow)
 }
 
 // Row allocator: pop the free stack (filled only by delete kernels, which never
@@ -196,7 +205,15 @@ __device__ __forceinline__ uint32_t alloc_row(const TableView& t) {
     if (top > 0) return t.free_rows[top - 1];
     atomicAdd(reinterpret_cast<unsigned long long*>(&t.ctr->free_top), 1ULL);
   }
-  return (uint32_t)atomicAdd(&t.ctr->rows_bump, 1ULL);
+  const unsigned long long r = atomicAdd(&t.ctr->rows_bump, 1ULL);
+  if (r >= t.rows_cap) {
+    // CUDA-graph replays inserted more keys than the host reserved for (the host books nothing
+    // during replay).  Never touch unmapped memory: park the key on the last mapped row and
+    // raise the sticky flag - the next host-side call on the table fails loudly.
+    atomicOr(&t.ctr->overflow, 1u);
+    return (uint32_t)(t.rows_cap - 1);
+  }
+  return (uint32_t)r;
 }
 
 __device__ __forceinline__ float* row_ptr(const TableView& t, uint32_t ctl) {

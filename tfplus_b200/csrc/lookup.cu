@@ -113,7 +113,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
     long long pos = -1;
     uint32_t ctl = 0;
 
-    if (valid && key == KEY_PAD) {
+    if (valid && key_reserved(key)) {
       mode = SEG ? M_SKIP : M_ZERO;  // padding id of the shard exchange: no table access
     } else if (valid) {
       Slot s;
@@ -322,7 +322,7 @@ gather_bulk_kernel(TableView t, const long long* __restrict__ ids,
     float* claim_row = nullptr;
     long long pos = -1;
     uint32_t ctl = 0;
-    if (valid && key == KEY_PAD) {
+    if (valid && key_reserved(key)) {
       mode = M_ZERO;  // padding id of the shard exchange: zeros, no table access
     } else if (valid) {
       Slot s;
@@ -494,7 +494,7 @@ scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __re
     uint32_t ctl = 0;
     int cnt = 1, off0 = 0;
     if (valid && PLANNED) { cnt = counts[i]; off0 = seg_off[i]; }
-    if (valid && key != KEY_PAD) {
+    if (valid && !key_reserved(key)) {
       Slot s;
       bool claimed;
       pos = find_or_claim(t, key, &s, &claimed);

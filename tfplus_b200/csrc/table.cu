@@ -291,12 +291,16 @@ TableView Table::view() const {
   v.enter_threshold = enter_threshold;
   v.ctr = d_ctr;
   v.free_rows = d_free;
+  v.rows_cap = rows_mapped;
   return v;
 }
 
 int Table::sync_counters(cudaStream_t stream) {
   KV_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
   KV_CUDA(cudaStreamSynchronize(stream));
+  if (h_ctr->overflow != 0)
+    return fail(2, "KvVariable: the table overflowed while captured work was replayed (more new "
+                   "keys than kv_reserve made room for); its contents are invalid");
   return 0;
 }
 

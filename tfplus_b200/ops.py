@@ -381,8 +381,9 @@ def kv_variable_export(table_handle, first_n=3, enable_cutoff=False, cutoff_valu
   freq_keys = torch.empty(nf.value, dtype=torch.int64, device=dev)
   u32 = freq_dtype in (torch.uint32, torch.int32)
   freq_values = torch.empty(nf.value, dtype=torch.int32 if u32 else torch.uint16, device=dev)
-  check(h._lib.kv_export(h.ptr, first_n, _ptr(keys), _ptr(values), _ptr(blacklist),
-                         _ptr(freq_keys), _ptr(freq_values), int(u32), h.stream))
+  check(h._lib.kv_export_bounded(h.ptr, first_n, _ptr(keys), _ptr(values), nk.value,
+                                 _ptr(blacklist), nb.value, _ptr(freq_keys), _ptr(freq_values),
+                                 nf.value, int(u32), h.stream))
   if first_n > 3:
     rows = C.c_int64()
     check(h._lib.kv_init_table_rows(h.ptr, C.byref(rows)))
@@ -391,6 +392,12 @@ def kv_variable_export(table_handle, first_n=3, enable_cutoff=False, cutoff_valu
   else:
     init_table = torch.empty((0, h.dim), dtype=torch.float32, device=dev)
   return keys, values, init_table, blacklist, freq_keys, freq_values
+
+
+def kv_variable_check_overflow(table_handle):
+  """Raises if CUDA-graph replays inserted more keys than kv_variable_reserve made room for."""
+  h = table_handle
+  check(h._lib.kv_check_overflow(h._live(), h.stream))
 
 
 def kv_variable_enable_delta_export(table_handle, support_prediction_delta=False):

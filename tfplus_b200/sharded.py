@@ -243,10 +243,20 @@ class PaddedShardedStep:
     self._a2a(self.g_recv, self.g_send)
     ops.unsorted_segment_sum(self.g_recv, self.o_idx, self.o_num, out=self.o_gsum,
                              accumulate=True)
-    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, self.o_uniq,
-                                                   self.hpt, num_indices=self.o_num,
-                                                   advance_powers=True)
+    self._apply(self.o_gsum, self.o_uniq, self.o_num)
     return out
+
+  optimizer = "group_adam"   # or "adam": tfplus-Adam on an [m | v] slot (BASELINE config 4)
+
+  def _apply(self, gsum, uniq, num):
+    """The owner's fused apply over the gradient sums of the ids it owns; hpt holds the op's
+    scalar inputs in op order, beta^t advanced in the launch."""
+    if self.optimizer == "adam":
+      ops.kv_variable_sparse_apply_adam_dev(self.var, self.slot, gsum, uniq, self.hpt,
+                                            num_indices=num, advance_powers=True)
+    else:
+      ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, gsum, uniq, self.hpt,
+                                                     num_indices=num, advance_powers=True)
 
   def overflowed(self):
     return bool(self.route["overflow"].item())
@@ -368,9 +378,7 @@ class PeerShardedStep(PaddedShardedStep):
     O = self.osets[p]
     ops.unsorted_segment_sum(self.grads_in[p], O["idx"], O["num"], out=self.o_gsum,
                              accumulate=True)
-    ops.kv_variable_group_sparse_apply_adam_v4_dev(self.var, self.slot, self.o_gsum, O["uniq"],
-                                                   self.hpt, num_indices=O["num"],
-                                                   advance_powers=True)
+    self._apply(self.o_gsum, O["uniq"], O["num"])
 
   def run(self, ids, grad, out=None):
     B, G, C, D = self.batch, self.world, self.cap, self.dim
