@@ -1,8 +1,13 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --config dcn --steps 200 --warmup 10 > gpurun_out/r02_bench_dcn.json 2> gpurun_out/cfg_dcn.err || tail -5 gpurun_out/cfg_dcn.err
-python bench.py --config streaming --steps 200 --warmup 5 > gpurun_out/r02_bench_streaming.json 2> gpurun_out/cfg_streaming.err || tail -5 gpurun_out/cfg_streaming.err
-for c in dcn streaming; do python -c "
+N=${1:-2}
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"
+$T bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/n$N.err || tail -5 gpurun_out/n$N.err
+$T bench.py --gpus $N --config sharded200m --steps 64 --warmup 5 > gpurun_out/r02_bench_sharded200m_n$N.json 2> gpurun_out/s200n$N.err || tail -5 gpurun_out/s200n$N.err
+python - $N <<'PY'
 import json,sys
-d=json.load(open('gpurun_out/r02_bench_$c.json'))
-print('$c', round(d['value']/1e6,2),'M keys/s', round(d['ms_per_step']*1e3,1),'us frac', round(d['roofline']['frac'],4), 'cpu', (d.get('cpu_baseline') or {}).get('value'), d.get('checkpoint_round_trips'), d.get('keys_evicted'), d.get('table_size_after'), d.get('wall_ms_per_step'))
-"; done
+N=sys.argv[1]
+d=json.load(open('gpurun_out/r02_bench_n%s.json'%N))
+print('n'+N, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], (d['parity_check'].get('error') or '')[:300], d['nvlink']['bus_gbs_per_gpu'])
+d=json.load(open('gpurun_out/r02_bench_sharded200m_n%s.json'%N))
+print('s200 n'+N, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), d.get('hbm_used_gb'))
+PY
