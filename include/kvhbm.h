@@ -305,6 +305,15 @@ int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx,
                    int64_t n, int dim, int64_t max_segments,
                    const int32_t* d_num_segments, float* d_out, int accumulate,
                    kv_stream stream);
+/* The combiner of embedding_lookup_sparse (python/ops/embedding_ops.py:403-441) in one launch:
+ * d_out[r, :] = combine over the entries i with d_segment_ids[i] == r (sorted, as SparseTensor
+ * indices are) of d_emb[d_idx[i], :] * (d_weights ? d_weights[i] : 1); combiner 0 sum, 1 mean
+ * (divide by the weight sum / the count), 2 sqrtn (divide by sqrt of the sum of squared weights /
+ * sqrt(count)).  d_emb are the rows of the DISTINCT ids, d_idx the inverse index of kv_unique.
+ * Entries are added in increasing position (TF's CPU order); rows without entries are zero. */
+int kv_sparse_combine(const float* d_emb, const int32_t* d_idx, const int64_t* d_segment_ids,
+                      const float* d_weights, int64_t nnz, int64_t n_rows, int dim, int combiner,
+                      float* d_out, kv_stream stream);
 /* d_out[0 .. min(max_rows, *d_num_rows)) [dim] = 0. */
 int kv_zero_rows(float* d_out, int64_t max_rows, const int32_t* d_num_rows, int dim,
                  kv_stream stream);

@@ -65,6 +65,38 @@ def test_embedding_lookup_sparse_sum_mean():
   assert (e1 == 4950.0).all() and (e2 == 49.5).all()
 
 
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("dim", [1, 16, 300])
+def test_sparse_combine_kernel_is_the_sequential_reduction(combiner, weighted, dim):
+  # embedding_ops.py:403-441: segment_sum of (weighted) rows, / segment_sum(w) or / sqrt(segment_sum(w^2));
+  # entries added in increasing position, rows without entries zero
+  rng = np.random.default_rng(dim)
+  n_rows, U = 37, 50
+  seg = np.sort(rng.integers(0, n_rows, size=400)).astype(np.int64)
+  seg = seg[seg != 5]                                  # an empty row
+  idx = rng.integers(0, U, size=seg.size).astype(np.int32)
+  emb = rng.normal(size=(U, dim)).astype(np.float32)
+  w = rng.random(seg.size).astype(np.float32) + 0.5 if weighted else None
+  got = ops.sparse_combine(torch.from_numpy(emb).cuda(), torch.from_numpy(idx).cuda(),
+                           torch.from_numpy(seg).cuda(),
+                           None if w is None else torch.from_numpy(w).cuda(), n_rows,
+                           combiner).cpu().numpy()
+  want = np.zeros((n_rows, dim), np.float32)
+  den = np.zeros(n_rows, np.float32)
+  for i in range(seg.size):
+    wi = np.float32(1.0) if w is None else w[i]
+    want[seg[i]] += emb[idx[i]] * wi if w is not None else emb[idx[i]]
+    den[seg[i]] += wi * wi if combiner == "sqrtn" else wi
+  if combiner == "sqrtn":
+    den = np.sqrt(den)
+  if combiner != "sum":
+    nz = den > 0
+    want[nz] = want[nz] / den[nz, None]
+  np.testing.assert_array_equal(got, want)
+  assert not got[5].any()
+
+
 def test_safe_embedding_lookup_sparse_negative_id_is_valid():
   # py_ut/tests/test_embedding_ops.py:301-337
   params, _ = _const_weights(2, dim=8)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "kv_import": [vp, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, vp],
     "kv_delete": [vp, vp, i64, vp],
     "kv_check_overflow": [vp, vp],
+    "kv_sparse_combine": [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp],
     "kv_enable_delta_export": [vp, i32],
     "kv_delta_size": [vp, vp, C.POINTER(i64)],
     "kv_delta_export_count": [vp, i32, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),

@@ -78,6 +78,9 @@ int do_export(Table*, int, int64_t*, float*, int64_t*, int64_t*, void*, int, cud
 int do_import(Table*, const int64_t*, const float*, int64_t, const float*, int64_t, const int64_t*,
               int64_t, const int64_t*, const void*, int64_t, int, cudaStream_t);
 int do_delete(Table*, const int64_t*, int64_t, cudaStream_t);
+int do_sparse_combine(const float* emb, const int32_t* idx, const int64_t* seg, const float* w,
+                      int64_t nnz, int64_t n_rows, int dim, int combiner, float* out,
+                      cudaStream_t st);
 int do_delete_older(Table*, int, uint16_t, int64_t*, int64_t, cudaStream_t, int64_t*, Table* delta_set);
 int do_delta_mark(Table* set, const int64_t* ids, int64_t n, const int32_t* d_n, Table* main,
                   bool filter, cudaStream_t st);
@@ -610,6 +613,15 @@ int kv_segment_sum(kv_workspace* ws, const float* d_data, const int32_t* d_idx, 
           "segment_sum: bad arguments");
   return do_segment_sum(ws->w, d_data, d_idx, n, dim, max_segments, d_num_segments, d_out,
                         accumulate, S(stream));
+}
+int kv_sparse_combine(const float* d_emb, const int32_t* d_idx, const int64_t* d_segment_ids,
+                      const float* d_weights, int64_t nnz, int64_t n_rows, int dim, int combiner,
+                      float* d_out, kv_stream stream) {
+  KV_NEED(nnz >= 0 && n_rows >= 0 && dim > 0 && (n_rows == 0 || d_out) &&
+              (nnz == 0 || (d_emb && d_idx && d_segment_ids)),
+          "sparse_combine: bad arguments");
+  return do_sparse_combine(d_emb, d_idx, d_segment_ids, d_weights, nnz, n_rows, dim, combiner, d_out,
+                           S(stream));
 }
 int kv_zero_rows(float* d_out, int64_t max_rows, const int32_t* d_num_rows, int dim,
                  kv_stream stream) {

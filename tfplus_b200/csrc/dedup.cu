@@ -1118,6 +1118,74 @@ int do_plan_build(Plan* p, Workspace* ws, const int64_t* ids, int64_t n, cudaStr
   return 0;
 }
 
+// ---- embedding_lookup_sparse combiner ---------------------------------------------------------
+// python/ops/embedding_ops.py:403-441: after unique -> gather, the rows of the distinct ids are
+// expanded through the inverse index, optionally weighted, and reduced per SparseTensor row:
+// sparse_segment_sum / mean / sqrt_n (no weights) or segment_sum of weighted rows divided by
+// segment_sum(w) / sqrt(segment_sum(w^2)).  One warp per output row: the row's entries are a
+// contiguous run of `seg` (SparseTensor indices are row-major sorted), found by binary search,
+// and added in increasing position - the order of TF's CPU kernels - so the result does not
+// depend on scheduling.  Rows without entries are zero.
+__global__ void __launch_bounds__(256)
+sparse_combine_kernel(const float* __restrict__ emb, const int* __restrict__ idx,
+                      const long long* __restrict__ seg, const float* __restrict__ w,
+                      long long nnz, long long n_rows, int dim, int combiner,
+                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (; r < n_rows; r += nw) {
+    long long lo = 0, hi = nnz;          // first entry with seg >= r
+    while (lo < hi) { const long long m = (lo + hi) >> 1; if (__ldg(seg + m) < r) lo = m + 1; else hi = m; }
+    const long long first = lo;
+    hi = nnz;                            // first entry with seg > r
+    while (lo < hi) { const long long m = (lo + hi) >> 1; if (__ldg(seg + m) <= r) lo = m + 1; else hi = m; }
+    const long long last = lo;
+    float den = 0.f;
+    for (long long i = first; i < last; ++i) {
+      const float wi = w ? __ldg(w + i) : 1.0f;
+      den += combiner == 2 ? wi * wi : wi;
+    }
+    if (combiner == 2) den = sqrtf(den);
+    for (int c0 = 0; c0 < dim; c0 += 32 * 8) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      for (long long i = first; i < last; ++i) {
+        const float* row = emb + (long long)__ldg(idx + i) * dim;
+        const float wi = w ? __ldg(w + i) : 1.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = c0 + q * 32 + lane;
+          if (c < dim) acc[q] += w ? row[c] * wi : row[c];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = c0 + q * 32 + lane;
+        if (c < dim) {
+          float v = acc[q];
+          if (combiner != 0) v = last > first ? v / den : 0.f;
+          out[r * dim + c] = v;
+        }
+      }
+    }
+  }
+}
+
+int do_sparse_combine(const float* emb, const int32_t* idx, const int64_t* seg, const float* w,
+                      int64_t nnz, int64_t n_rows, int dim, int combiner, float* out,
+                      cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  if (combiner < 0 || combiner > 2) return fail(1, "combiner must be one of 'mean', 'sqrtn' or 'sum'");
+  int dev = 0;
+  KV_CUDA(cudaGetDevice(&dev));
+  sparse_combine_kernel<<<blocks_for(n_rows * 32, 256, dev), 256, 0, st>>>(
+      emb, idx, reinterpret_cast<const long long*>(seg), w, nnz, n_rows, dim, combiner, out);
+  KV_LAUNCHED();
+  return 0;
+}
+
 Workspace* workspace_new() {
   Workspace* w = new Workspace();
   cudaGetDevice(&w->device);

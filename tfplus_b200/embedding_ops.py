@@ -68,23 +68,12 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights=None, partition_strategy=
   else:
     (uniq, idx), counts = ops.unique(values), None
   emb = embedding_lookup(params, uniq, partition_strategy, max_norm=max_norm, counts=counts)
-  rows = emb.index_select(0, idx.long())
   w = None
   if sp_weights is not None:
     w = torch.as_tensor(sp_weights[1] if isinstance(sp_weights, tuple) else sp_weights,
                         dtype=torch.float32).to(dev)
-    rows = rows * w[:, None]
-  out = torch.zeros(n_rows, rows.shape[1], device=dev).index_add_(0, seg, rows)
-  if combiner == "sum":
-    return out
-  ones = torch.ones_like(seg, dtype=torch.float32) if w is None else w
-  if combiner == "mean":
-    den = torch.zeros(n_rows, device=dev).index_add_(0, seg, ones)
-  elif combiner == "sqrtn":
-    den = torch.zeros(n_rows, device=dev).index_add_(0, seg, ones * ones).sqrt()
-  else:
-    raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
-  return out / den.clamp_min(1e-12)[:, None] * (den > 0)[:, None]
+  # expand through the inverse index, weight, reduce per row, normalise: one kernel
+  return ops.sparse_combine(emb.reshape(uniq.numel(), -1), idx, seg, w, n_rows, combiner)
 
 
 def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=None,

@@ -394,6 +394,26 @@ def kv_variable_export(table_handle, first_n=3, enable_cutoff=False, cutoff_valu
   return keys, values, init_table, blacklist, freq_keys, freq_values
 
 
+_COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
+
+
+def sparse_combine(emb, idx, segment_ids, weights, n_rows, combiner):
+  """The combiner half of embedding_lookup_sparse (embedding_ops.py:403-441) as one kernel:
+  emb[U, D] rows of the distinct ids, idx[nnz] inverse index, segment_ids[nnz] sorted row ids."""
+  if combiner not in _COMBINERS:
+    raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
+  emb = emb.contiguous()
+  idx = idx.to(torch.int32).contiguous()
+  seg = segment_ids.to(torch.int64).contiguous()
+  w = None if weights is None else weights.to(torch.float32).contiguous()
+  out = torch.empty((int(n_rows), emb.shape[1]), dtype=torch.float32, device=emb.device)
+  with torch.cuda.device(emb.device):
+    check(_lib.load().kv_sparse_combine(emb.data_ptr(), idx.data_ptr(), seg.data_ptr(), _ptr(w),
+                                        idx.numel(), int(n_rows), emb.shape[1],
+                                        _COMBINERS[combiner], out.data_ptr(), _stream(emb.device)))
+  return out
+
+
 def kv_variable_check_overflow(table_handle):
   """Raises if CUDA-graph replays inserted more keys than kv_variable_reserve made room for."""
   h = table_handle
