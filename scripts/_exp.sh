@@ -1,13 +1,10 @@
 cd $GRAFT_REPO_ROOT
-N=${1:-2}
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"
-$T bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/n$N.err || tail -5 gpurun_out/n$N.err
-$T bench.py --gpus $N --config sharded200m --steps 64 --warmup 5 > gpurun_out/r02_bench_sharded200m_n$N.json 2> gpurun_out/s200n$N.err || tail -5 gpurun_out/s200n$N.err
-python - $N <<'PY'
-import json,sys
-N=sys.argv[1]
-d=json.load(open('gpurun_out/r02_bench_n%s.json'%N))
-print('n'+N, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], (d['parity_check'].get('error') or '')[:300], d['nvlink']['bus_gbs_per_gpu'])
-d=json.load(open('gpurun_out/r02_bench_sharded200m_n%s.json'%N))
-print('s200 n'+N, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), d.get('hbm_used_gb'))
-PY
+mkdir -p /tmp/ncu
+for k in apply_plan_kernel stage_heavy_kernel expand_plan_kernel unique_insert_kernel plan_sort_kernel; do
+  ncu --set full --clock-control none -k regex:$k -s 3 -c 1 -o /tmp/ncu/r02_ncu_$k python scripts/profile_step.py --steps 5 > /tmp/ncu/ncu_$k.log 2>&1
+done
+ncu --set full --clock-control none -k regex:gather_kernel -s 30 -c 1 -o /tmp/ncu/r02_ncu_gather_kernel python scripts/profile_step.py --steps 5 > /tmp/ncu/ncu_gather_kernel.log 2>&1
+python scripts/ncu_summary.py --json /tmp/ncu/*.ncu-rep > gpurun_out/r02_ncu_kernels.txt 2>&1
+cp profiles/ncu_traffic.json gpurun_out/ncu_traffic.json
+cp /tmp/ncu/r02_ncu_apply_plan_kernel.ncu-rep gpurun_out/
+tail -3 gpurun_out/r02_ncu_kernels.txt; du -sh gpurun_out

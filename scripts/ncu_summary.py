@@ -2,6 +2,7 @@
 """Prints the handful of ncu metrics we track from a .ncu-rep (run where ncu is installed)."""
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -20,18 +21,53 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_sector_hit_rate.pct", "launch__waves_per_multiprocessor"]
 
 
-def main(path):
+UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+# bench.py stage -> substring of the kernel that dominates it
+STAGE_KERNELS = {"segment_sum+apply": "apply_plan_kernel", "gather": "expand_plan_kernel",
+                 "unique": "unique_insert_kernel"}
+
+
+def main(path, traffic):
   out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"]).decode()
   rows = list(csv.reader(io.StringIO(out)))
   hdr, units, data = rows[0], rows[1], rows[2:]
   for r in data:
     d = dict(zip(hdr, r))
-    print("== %s  grid %s block %s" % (d.get("Kernel Name", "?")[:80], d.get("Grid Size"), d.get("Block Size")))
+    name = d.get("Kernel Name", "?")
+    print("== %s  grid %s block %s" % (name[:80], d.get("Grid Size"), d.get("Block Size")))
     for k in KEYS:
       if k in d:
         print("   %-75s %s %s" % (k, d[k], units[hdr.index(k)]))
+    try:
+      tot = 0.0
+      for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(d[k].replace(",", "")) * UNIT_BYTES[units[hdr.index(k)]]
+      for stage, sub in STAGE_KERNELS.items():
+        if sub in name:
+          traffic[stage] = {"name": name.split("(")[0][-70:], "dram_bytes": tot,
+                            "duration_us": float(d["gpu__time_duration.sum"].replace(",", "")) *
+                            {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1.0),
+                            "report": os.path.basename(path)}
+    except (KeyError, ValueError):
+      pass
 
 
 if __name__ == "__main__":
-  for p in sys.argv[1:]:
-    main(p)
+  import json
+  import os
+  args = [a for a in sys.argv[1:] if not a.startswith("--")]
+  traffic = {}
+  for p in args:
+    main(p, traffic)
+  if "--json" in sys.argv:
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+      git = subprocess.check_output(["git", "-C", root, "rev-parse", "--short", "HEAD"]).decode().strip()
+    except Exception:
+      git = None
+    dst = os.path.join(root, "profiles", "ncu_traffic.json")
+    json.dump({"git": git, "how": "ncu --set full --clock-control none, one launch per kernel, "
+               "dram__bytes_read.sum + dram__bytes_write.sum", "kernels": traffic},
+              open(dst, "w"), indent=1)
+    print("wrote", dst)
