@@ -507,7 +507,11 @@ class LocalStepper:
     self.hp = torch.tensor([HP["lr"], HP["beta1"], HP["beta2"], HP["beta1"], HP["beta2"],
                             HP["epsilon"], HP["l1"], HP["l2"], HP["l21"]], dtype=torch.float32,
                            device=dev)
-    self.side = torch.cuda.Stream(device=dev)
+    # the chain runs on a high-priority stream, the look-ahead plan build on a low-priority one:
+    # when both have blocks to place, the chain's go first
+    prio = os.environ.get("KVHBM_BENCH_PRIORITY", "1") != "0"
+    self.side = torch.cuda.Stream(device=dev, priority=0)
+    self.chain = torch.cuda.Stream(device=dev, priority=-1 if prio else 0)
     self.lookahead = os.environ.get("KVHBM_BENCH_PLAN_AHEAD", "1") != "0"
 
   def populate(self):
@@ -537,7 +541,8 @@ class LocalStepper:
   def _capture(self, fn):
     torch = self.torch
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    self.chain.wait_stream(torch.cuda.current_stream(self.dev))
+    with torch.cuda.graph(g, stream=self.chain):
       fn()
     return g
 

@@ -435,4 +435,98 @@ class KvDeleteOp : public OpKernel {
 };
 REGISTER_KERNEL_BUILDER(Name("KvVariableDelete").Device(DEVICE_GPU).HostMemory("table_handle"), KvDeleteOp);
 
+// KvVariableGetCountV2 / KvVariableGetTimeStamp (ops/kv_variable_ops.cc:349-358,687-696):
+// KvVariable::GetCount / GetTimeStamp, kernels/kv_variable.h:503-561.
+template <bool TIMESTAMP>
+class KvGetMetaOp : public OpKernel {
+ public:
+  using OpKernel::OpKernel;
+  void Compute(OpKernelContext* ctx) override {
+    KvHbmVariable* v;
+    OP_REQUIRES_OK(ctx, Lookup(ctx, 0, &v));
+    core::ScopedUnref unref(v);
+    const Tensor& ids = ctx->input(1);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, ids.shape(), &out));
+    const int64_t* d_ids = reinterpret_cast<const int64_t*>(ids.flat<int64_t>().data());
+    if (TIMESTAMP)
+      OP_REQUIRES_OK(ctx, FromKv(kv_get_timestamp(v->table(), d_ids, ids.NumElements(),
+                                                  out->flat<uint32_t>().data(), Today(), StreamOf(ctx))));
+    else
+      OP_REQUIRES_OK(ctx, FromKv(kv_get_count(v->table(), d_ids, ids.NumElements(),
+                                              out->flat<int32_t>().data(), StreamOf(ctx))));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("KvVariableGetCountV2").Device(DEVICE_GPU).HostMemory("table_handle")
+                            .TypeConstraint<int64_t>("Tindices"), KvGetMetaOp<false>);
+REGISTER_KERNEL_BUILDER(Name("KvVariableGetTimeStamp").Device(DEVICE_GPU).HostMemory("table_handle")
+                            .TypeConstraint<int64_t>("Tindices"), KvGetMetaOp<true>);
+
+// KvVariableDeleteWithTimestamp (ops/kv_variable_ops.cc:698-706): KvVariable::DeleteWithTimestamp,
+// kernels/kv_variable.h:756-789.  The output size is data dependent: a buffer as large as the
+// table is filled on the device, the count read back, the prefix copied out.
+class KvDeleteWithTimestampOp : public OpKernel {
+ public:
+  explicit KvDeleteWithTimestampOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("threshold", &threshold_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    KvHbmVariable* v;
+    OP_REQUIRES_OK(ctx, Lookup(ctx, 0, &v));
+    core::ScopedUnref unref(v);
+    int64_t cap = 0, n = 0;
+    OP_REQUIRES_OK(ctx, FromKv(kv_map_size(v->table(), StreamOf(ctx), &cap)));
+    Tensor tmp;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_INT64, TensorShape({cap > 0 ? cap : 1}), &tmp));
+    OP_REQUIRES_OK(ctx, FromKv(kv_delete_with_timestamp(
+        v->table(), threshold_, Today(), reinterpret_cast<int64_t*>(tmp.flat<int64_t>().data()), cap,
+        StreamOf(ctx), &n)));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({n}), &out));
+    if (n > 0)
+      cudaMemcpyAsync(out->flat<int64_t>().data(), tmp.flat<int64_t>().data(), n * sizeof(int64_t),
+                      cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(StreamOf(ctx)));
+  }
+ private:
+  int threshold_;
+};
+REGISTER_KERNEL_BUILDER(Name("KvVariableDeleteWithTimestamp").Device(DEVICE_GPU).HostMemory("table_handle")
+                            .TypeConstraint<int64_t>("Tkeys"), KvDeleteWithTimestampOp);
+
+// KvVariableFullOrDeltaExport (ops/kv_variable_ops.cc:633-660), delta mode: KvVariable::DeltaExport,
+// kernels/dynamic_save.hpp:197-449.  Eight outputs; sizes from kv_delta_export_count, buffers
+// bounded by them (entries a concurrent insert adds in between are dropped, not written).
+class KvDeltaExportOp : public OpKernel {
+ public:
+  explicit KvDeltaExportOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("first_n", &first_n_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    KvHbmVariable* v;
+    OP_REQUIRES_OK(ctx, Lookup(ctx, 0, &v));
+    core::ScopedUnref unref(v);
+    int64_t nk, nb, nf, nd, counts[4];
+    OP_REQUIRES_OK(ctx, FromKv(kv_delta_export_count(v->table(), first_n_, StreamOf(ctx), &nk, &nb, &nf, &nd)));
+    Tensor *keys, *values, *init, *black, *fk, *fv, *need_full, *del;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({nk}), &keys));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({nk, kv_dim(v->table())}), &values));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, TensorShape({0, kv_dim(v->table())}), &init));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, TensorShape({nb}), &black));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, TensorShape({nf}), &fk));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(5, TensorShape({nf}), &fv));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(6, TensorShape({1}), &need_full));   // HostMemory
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(7, TensorShape({nd}), &del));
+    need_full->flat<bool>()(0) = false;
+    OP_REQUIRES_OK(ctx, FromKv(kv_delta_export(
+        v->table(), first_n_, reinterpret_cast<int64_t*>(keys->flat<int64_t>().data()),
+        values->flat<float>().data(), nk, reinterpret_cast<int64_t*>(black->flat<int64_t>().data()), nb,
+        reinterpret_cast<int64_t*>(fk->flat<int64_t>().data()), fv->flat<uint32_t>().data(), nf,
+        reinterpret_cast<int64_t*>(del->flat<int64_t>().data()), nd, StreamOf(ctx), counts)));
+  }
+ private:
+  int first_n_;
+};
+REGISTER_KERNEL_BUILDER(Name("KvVariableFullOrDeltaExport").Device(DEVICE_GPU).HostMemory("table_handle")
+                            .HostMemory("need_full_import"), KvDeltaExportOp);
+
 }  // namespace tfplus_b200
