@@ -1,13 +1,7 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 200 --warmup 20 > gpurun_out/r02_bench_n1.json 2> gpurun_out/n1.err || tail -5 gpurun_out/n1.err
-python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1_k20.json 2> gpurun_out/n1b.err || tail -5 gpurun_out/n1b.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_n1_reference_arm.json 2>/dev/null
-python -c "
-import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python - <<'PY'
-import json
-for f in ('r02_bench_n1','r02_bench_n1_k20'):
-  d=json.load(open('gpurun_out/%s.json'%f))
-  print(f, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], round(d['roofline']['frac'],3), d['roofline']['traffic'], round(d['cpu_baseline']['value']/1e6,2), d['gpu_launches'])
-d=json.load(open('gpurun_out/r02_bench_n1_reference_arm.json')); print('ref', d['value']/1e6)
-PY
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for p in 1 0; do KVHBM_PDL=$p python bench.py --steps 192 --warmup 10 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('pdl $p', round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), {k:round(v['ms']*1e3,1) for k,v in d['roofline']['stages'].items()}, d['parity_check']['ok'])
+"; done

@@ -92,6 +92,7 @@ struct Ring {
 template <int VEC>
 __global__ void __launch_bounds__(256)
 stage_heavy_kernel(const __grid_constant__ PlanView pl, const float* __restrict__ grad, int dim) {
+  pdl_wait();
   const long long n = pl.n;
   const long long units = (n + 3) >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -287,6 +288,7 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
                   const __grid_constant__ TableView sb, const __grid_constant__ PlanView pl,
                   const float* __restrict__ grad, const __grid_constant__ ApplyParams p_in,
                   const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv) {
+  pdl_wait();
   ApplyParams p = p_in;
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p_in.update_slots);
   extern __shared__ __align__(128) unsigned char ring[];   // ring, then the light path's staging
@@ -528,8 +530,8 @@ int launch_stage_heavy(const PlanView& pv, const float* data, int dim, int devic
   const long long cap = (long long)sm_count(device) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (vec == 4) stage_heavy_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(pv, data, dim);
-  else stage_heavy_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(pv, data, dim);
+  if (vec == 4) KV_CUDA(launch_pdl(stage_heavy_kernel<4>, dim3((unsigned)blocks), dim3(256), 0, st, pv, data, dim));
+  else KV_CUDA(launch_pdl(stage_heavy_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, pv, data, dim));
   KV_LAUNCHED();
   return 0;
 }
@@ -570,8 +572,8 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
   }
   TableView vb = sb ? sb->view() : sa->view();
   KV_TRY(launch_stage_heavy(pv, grad, var->dim, var->device, st));
-  kern<<<(unsigned)blocks, AP_THREADS, smem, st>>>(var->view(), sa->view(), vb, pv, grad, p, d_hp,
-                                                  today, tpr, kpw, d_adv);
+  KV_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AP_THREADS), smem, st, var->view(), sa->view(), vb,
+                     pv, grad, p, d_hp, (uint32_t)today, tpr, kpw, d_adv));
   KV_LAUNCHED();
   return 0;
 }

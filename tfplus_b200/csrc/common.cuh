@@ -56,6 +56,13 @@ struct Counters {
                                   // past what kv_reserve made room for; reported by the host
 };
 
+// Entry of a kernel that may have been launched with programmatic stream serialization: wait for
+// the previous kernel of the stream (completed and flushed), then let the next one be scheduled.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // What a kernel needs to know about one table; passed by value.
 struct TableView {
   Slot* slots;

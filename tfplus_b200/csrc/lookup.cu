@@ -75,6 +75,7 @@ gather_kernel(TableView t, const long long* __restrict__ ids, const int* __restr
               long long n, float* __restrict__ out, uint32_t today, int tpr, int kpw, int flags,
               float* const* __restrict__ seg_out, int seg_len, const int* __restrict__ d_n,
               uint2* __restrict__ hint) {
+  pdl_wait();
   if (d_n) { const long long dn = *d_n; if (dn < n) n = dn; }  // count produced on the device
   // flags bit 1: frequencies untouched; bit 2: no row output at all — the caller only wants
   // the keys resolved (inserted, counted) and `hint[i]` = {slot, ctl} of id i, and moves the
@@ -815,10 +816,11 @@ int launch_gather(Table* tb, bool insert, const int64_t* ids, const int32_t* cou
   const long long warps = (n + kpw - 1) / kpw;
   const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const long long* k = reinterpret_cast<const long long*>(ids);
-#define KV_G(INS) gather_kernel<VEC, CPL, INS, 8, false><<<blocks, bs, 0, st>>>(tb->view(), k, counts, n, out, today, tpr, kpw, flags, nullptr, 0, d_n, hint)
+#define KV_G(INS) KV_CUDA(launch_pdl(gather_kernel<VEC, CPL, INS, 8, false>, dim3(blocks), dim3(bs), 0, st, tb->view(), k, counts, (long long)n, out, (uint32_t)today, tpr, kpw, flags, (float* const*)nullptr, 0, d_n, hint))
   if (seg_out) {
-    gather_kernel<VEC, CPL, true, 8, true><<<blocks, bs, 0, st>>>(
-        tb->view(), k, counts, n, nullptr, today, tpr, kpw, flags, seg_out, seg_len, d_n, hint);
+    KV_CUDA(launch_pdl(gather_kernel<VEC, CPL, true, 8, true>, dim3(blocks), dim3(bs), 0, st, tb->view(), k,
+                       counts, (long long)n, (float*)nullptr, (uint32_t)today, tpr, kpw, flags, seg_out,
+                       (int)seg_len, d_n, hint));
   } else if (insert) KV_G(true);
   else KV_G(false);
 #undef KV_G
@@ -871,6 +873,7 @@ __global__ void __launch_bounds__(256)
 expand_plan_kernel(TableView t, const int* __restrict__ idx, const uint2* __restrict__ hint,
                    const int* __restrict__ first, long long n, float* __restrict__ out, int tpr,
                    int kpw) {
+  pdl_wait();
   constexpr int UNR = 8 / CPL > 0 ? 8 / CPL : 1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -961,9 +964,11 @@ int launch_expand_plan(Table* tb, bool insert, const PlanView& pv, const int* fi
   const int blocks = blocks_for(warps * 32, bs, tb->device, 2048 / bs);
   const uint2* hint = reinterpret_cast<const uint2*>(pv.hint);
   if (insert)
-    expand_plan_kernel<VEC, CPL, true><<<blocks, bs, 0, st>>>(tb->view(), pv.idx, hint, first, n, out, tpr, kpw);
+    KV_CUDA(launch_pdl(expand_plan_kernel<VEC, CPL, true>, dim3(blocks), dim3(bs), 0, st, tb->view(), pv.idx,
+                       hint, first, n, out, tpr, kpw));
   else
-    expand_plan_kernel<VEC, CPL, false><<<blocks, bs, 0, st>>>(tb->view(), pv.idx, hint, first, n, out, tpr, kpw);
+    KV_CUDA(launch_pdl(expand_plan_kernel<VEC, CPL, false>, dim3(blocks), dim3(bs), 0, st, tb->view(), pv.idx,
+                       hint, first, n, out, tpr, kpw));
   KV_LAUNCHED();
   return 0;
 }

@@ -1,4 +1,6 @@
 // table.cu — host-side table management: allocation, growth, rehash.
+#include <cstdlib>
+
 #include "table.h"
 
 #include <atomic>
@@ -233,6 +235,11 @@ static uint64_t pow2_at_least(uint64_t x) {
 
 void plan_delete(Plan*);
 void workspace_delete(Workspace*);
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("KVHBM_PDL") && atoi(getenv("KVHBM_PDL")) == 0);
+  return on;
+}
 
 Table::~Table() {
   cudaSetDevice(device);

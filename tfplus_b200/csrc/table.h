@@ -104,6 +104,27 @@ struct Table {
   int clear(cudaStream_t stream);
 };
 
+// Programmatic dependent launch for the kernels of the step's serial chain (lookup probe ->
+// expand -> staging -> fused apply -> next lookup): the next kernel's blocks are scheduled while
+// the previous kernel drains and wait in `griddepcontrol.wait` (pdl_wait(), first thing in the
+// kernel) until it has completed and flushed.  KVHBM_PDL=0 turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // launch geometry helpers
 int sm_count(int device);
 inline int blocks_for(int64_t work_items, int per_block, int device, int max_per_sm = 8) {

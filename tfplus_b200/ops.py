@@ -278,6 +278,20 @@ def kv_variable_gather_or_insert_with_counts(table_handle, indices, counts, out=
   return out
 
 
+def batch_kv_variable_gather_or_zeros_v2(table_handles, indices_list):
+  """Op `BatchKvVariableGatherOrZerosV2` (kernels/kv_variable_ops.cc:431-496): one read-only
+  lookup per (table, indices) pair."""
+  return [kv_variable_gather_or_zeros_v2(h, ids) for h, ids in zip(table_handles, indices_list)]
+
+
+def kv_variable_gather_v2(table_handle, indices, use_init_value=True):
+  """Legacy op `KvVariableGatherV2` (kernels/kv_variable_ops.cc:633-701): bool attr instead of two
+  ops - use_init_value inserts missing keys from the initializer, otherwise zeros."""
+  if use_init_value:
+    return kv_variable_gather_or_insert_v2(table_handle, indices)
+  return kv_variable_gather_or_zeros_v2(table_handle, indices)
+
+
 def kv_variable_insert_v2(table_handle, indices, values, filter_out=None, blacklist=None):
   """Op `KvVariableInsertV2` -> KvVariable::InsertOrUpdate."""
   h = table_handle
