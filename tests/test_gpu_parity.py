@@ -319,6 +319,65 @@ def test_get_count_and_get_timestamp():
   ops.set_today(TODAY)
 
 
+def test_reserved_key_values_are_padding():
+  # INT64_MIN / INT64_MIN + 1 are the table's empty / tombstone sentinels: lookups return zeros,
+  # nothing is inserted, no neighbour's frequency word is touched (deviation 5)
+  p = Pair(8, init=0.25)
+  lo = np.iinfo(np.int64).min
+  p.gather_or_insert(np.array([5, 6, 7], np.int64))
+  before = p.state_gpu()
+  ids = np.array([lo, lo + 1, 5, lo], np.int64)
+  rows = ops.kv_variable_gather_or_insert_v2(p.gpu, t(ids)).cpu().numpy()
+  assert not rows[[0, 1, 3]].any() and (rows[2] == 0.25).all()
+  assert not ops.kv_variable_gather_or_zeros_v2(p.gpu, t(ids[:2])).cpu().numpy().any()
+  ops.kv_variable_scatter_add_v2(p.gpu, t(ids[:2]), t(np.ones((2, 8), np.float32)))
+  after = p.state_gpu()
+  assert set(after["freq"]) == set(before["freq"]) == {5, 6, 7}
+  assert ops.kv_variable_size_v2(p.gpu) == 3
+  assert after["freq"][6] == before["freq"][6] and after["freq"][7] == before["freq"][7]
+
+
+def test_replay_past_the_reservation_is_reported_not_corrupting():
+  # captured work books nothing on the host: a graph that keeps inserting new keys eventually
+  # outruns kv_reserve; the kernels then raise the sticky overflow flag instead of touching
+  # unmapped rows, and the next counter read fails loudly
+  dim = 8
+  h = ops.kv_variable(value_shape=[dim], device=DEV, seed=3, capacity_hint=64)
+  ops.init_kv_variable_v2(h, torch.ones(4, dim, device=DEV))
+  ids = torch.arange(0, 4096, dtype=torch.int64, device=DEV)
+  out = torch.empty((4096, dim), device=DEV)
+  step = torch.zeros(1, dtype=torch.int64, device=DEV)
+  ops.kv_variable_gather_or_insert_v2(h, ids, out=out)          # eager once: sizes everything
+  ops.kv_variable_reserve(h, 4096)
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    ids.add_(4096)                                              # 4096 never-seen keys per replay
+    ops.kv_variable_gather_or_insert_v2(h, ids, out=out)
+  g.replay()                                                    # fits the reservation
+  torch.cuda.synchronize()
+  ops.kv_variable_check_overflow(h)
+  for _ in range(2000):                                         # 8 M more keys: far past it
+    g.replay()
+  torch.cuda.synchronize()
+  with pytest.raises(Exception, match="overflow"):
+    ops.kv_variable_check_overflow(h)
+  del g, step
+
+
+def test_scatter_with_duplicates_needs_one_eager_call_before_capture():
+  p = Pair(8)
+  ids = t(np.array([1, 1, 2], np.int64))
+  upd = t(np.ones((3, 8), np.float32))
+  g = torch.cuda.CUDAGraph()
+  with pytest.raises(Exception):
+    with torch.cuda.graph(g):
+      ops.kv_variable_scatter_add_v2(p.gpu, ids, upd)           # its dedup plan is not sized yet
+  torch.cuda.synchronize()
+  ops.kv_variable_scatter_add_v2(p.gpu, ids, upd)               # eager: sizes the plan
+  p.cpu.scatter("add", np.array([1, 1, 2], np.int64), np.ones((3, 8), np.float32))
+  p.check_state()
+
+
 def test_scatter_with_duplicate_ids():
   # GradientDescentOptimizer._resource_apply_sparse_duplicate_indices hands scatter_add the raw
   # indices: ScatterUpdate (kv_variable.h:616-734) applies every occurrence, on new and on
