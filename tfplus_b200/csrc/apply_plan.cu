@@ -368,17 +368,25 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
     GradSrc gs;
     gs.grad = grad; gs.row0 = 0; gs.counts = pl.counts; gs.seg_off = pl.seg_off; gs.pos = pl.pos;
     gs.heavy_t = pl.heavy_t; gs.hint = pl.hint; gs.cg = false;
-    const long long ngroups = (U + kpw - 1) / kpw;
-    gs.stride = ngroups;
+    // Guided sizes: the first three quarters of the ranks go out in groups of `kpw` ids, the
+    // last quarter in groups of one round (32 / tpr ids) - what is still unclaimed when the pool
+    // runs dry costs the launch one group-time, so the last groups are the short ones.  Both
+    // ranges are handed out strided (group g takes ranks g, g + G, g + 2G, ...).
+    const int kpi_l = 32 / tpr;
+    const long long UA = kpw > kpi_l ? U - U / 4 : U;
+    const long long GA = (UA + kpw - 1) / kpw;
+    const long long GB = (U - UA + kpi_l - 1) / kpi_l;
     for (;;) {
-      const long long base = next_light_group(pl.work, 1, lane);   // group g: ids g, g + G, g + 2G, ...
-      if (base >= ngroups) break;
+      const long long g = next_light_group(pl.work, 1, lane);
+      if (g >= GA + GB) break;
 #ifdef KVHBM_TRACE
       if (trace && n_groups == 0) gs.trace = trace + 131072 + ((size_t)blockIdx.x * AP_NW + wib) * 16;
       else gs.trace = nullptr;
 #endif
-      apply_group<AP_NW, VEC, CPL, KIND, 1, 4>(sm, wib, var, sa, sb, ids, gs, base, U, p, today, tpr,
-                                               kpw, false);
+      const bool first = g < GA;
+      gs.stride = first ? GA : GB;
+      apply_group<AP_NW, VEC, CPL, KIND, 1, 4>(sm, wib, var, sa, sb, ids, gs, first ? g : UA + (g - GA),
+                                               first ? UA : U, p, today, tpr, first ? kpw : kpi_l, false);
 #ifdef KVHBM_TRACE
       ++n_groups;
 #endif
