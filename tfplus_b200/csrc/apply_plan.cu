@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1)
 apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__ TableView sa,
                   const __grid_constant__ TableView sb, const __grid_constant__ PlanView pl,
                   const float* __restrict__ grad, const __grid_constant__ ApplyParams p_in,
-                  const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv) {
+                  const float* __restrict__ d_hp, uint32_t today, int tpr, int kpw, float* d_adv,
+                  int guided) {
   pdl_wait();
   ApplyParams p = p_in;
   if (d_hp) p = derive_params<KIND>(d_hp, var.dim, p_in.update_slots);
@@ -373,7 +374,7 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
     // runs dry costs the launch one group-time, so the last groups are the short ones.  Both
     // ranges are handed out strided (group g takes ranks g, g + G, g + 2G, ...).
     const int kpi_l = 32 / tpr;
-    const long long UA = kpw > kpi_l ? U - U / 4 : U;
+    const long long UA = (guided && kpw > kpi_l) ? U - U / 4 : U;
     const long long GA = (UA + kpw - 1) / kpw;
     const long long GB = (U - UA + kpi_l - 1) / kpi_l;
     for (;;) {
@@ -554,6 +555,7 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
                       const ApplyParams& p, const float* d_hp, uint16_t today, cudaStream_t st,
                       int tpr, float* d_adv) {
   static const int kpw_env = getenv("KVHBM_APPLYP_KPW") ? atoi(getenv("KVHBM_APPLYP_KPW")) : 0;
+  static const int guided_env = getenv("KVHBM_APPLYP_GUIDED") ? atoi(getenv("KVHBM_APPLYP_GUIDED")) : 1;
   constexpr int bps_env = 1;
   const int sms = sm_count(var->device);
   const int kpi = 32 / tpr;
@@ -581,7 +583,7 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
   TableView vb = sb ? sb->view() : sa->view();
   KV_TRY(launch_stage_heavy(pv, grad, var->dim, var->device, st));
   KV_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(AP_THREADS), smem, st, var->view(), sa->view(), vb,
-                     pv, grad, p, d_hp, (uint32_t)today, tpr, kpw, d_adv));
+                     pv, grad, p, d_hp, (uint32_t)today, tpr, kpw, d_adv, guided_env));
   KV_LAUNCHED();
   return 0;
 }
