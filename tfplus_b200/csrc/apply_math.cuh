@@ -460,6 +460,9 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
   bool mine = valid;
   const long long ii = (valid && gs.remap) ? (long long)gs.remap[i] : i;   // index into ids / hint
   if (valid) key = ids[ii];
+  // the lookup's hint is indexed by rank, not by key: fetch it with the key, not after it
+  uint32_t hint_slot = 0xffffffffu;
+  if (valid && gs.hint) hint_slot = gs.hint[ii].x;
   int gp4[4] = {0, 0, 0, 0};
   if (valid && planned) {
     gcnt = gs.counts[i];
@@ -475,10 +478,7 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
     int rv = -1, ra = -1, rb = TWO ? -1 : 0;
     Slot sv, ssa, ssb, x0, x1, y0, y1, z0, z1;
     long long hpos = -1;
-    if (gs.hint) {
-      const uint32_t h = gs.hint[ii].x;
-      if (h != 0xffffffffu && (unsigned long long)h <= var.mask) hpos = (long long)h;
-    }
+    if (hint_slot != 0xffffffffu && (unsigned long long)hint_slot <= var.mask) hpos = (long long)hint_slot;
     if (hpos >= 0) x0 = load_slot(var.slots + hpos);
     for (unsigned long long guard = 0; guard <= var.mask + sa.mask + sb.mask; ++guard) {
       if (rv < 0 && hpos < 0) { x0 = load_slot(var.slots + pv.bucket * 2); x1 = load_slot(var.slots + pv.bucket * 2 + 1); }
