@@ -8,8 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkvhbm.so")
 SOURCES = ["table.cu", "lookup.cu", "apply.cu", "apply_plan.cu", "dedup.cu", "ckpt.cu", "peer.cu",
-           "capi.cu"]
+           "capi.cu"] + ["apply_plan_k%d.cu" % k for k in range(7)]   # one optimizer per unit
 HEADERS = ["common.cuh", "table.h", "plan.h", "apply_math.cuh", "async_copy.cuh",
+           "apply_plan_kernel.cuh",
            os.path.join("..", "..", "include", "kvhbm.h")]
 
 # -fmad=false: the reference's CPU build has no FMA contraction (configure.sh:136)
