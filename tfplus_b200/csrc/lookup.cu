@@ -509,7 +509,7 @@ scatter_kernel(TableView t, const long long* __restrict__ ids, const float* __re
           // a row pointer is only ever derived from a PUBLISHED ctl: with distinct ids a
           // found key is always published; should a caller break that contract, wait for
           // the claimer of this launch instead of touching row 0
-          for (int spin = 0; !(ctl & CTL_READY) && spin < (1 << 22); ++spin)
+          for (int spin = 0; !(ctl & CTL_READY) && spin < (1 << 14); ++spin)
             ctl = ld_acquire_u32(&t.slots[pos].ctl);
           if (!(ctl & CTL_READY) || (ctl & CTL_BLACK)) mode = M_SKIP;  // :690 blacklisted keys are skipped
           else { mode = M_COPY; row = row_ptr(t, ctl); }
@@ -605,7 +605,13 @@ insert_kernel(TableView t, const long long* __restrict__ ids, const float* __res
       pos = find_or_claim(t, key, &s, &claimed);
       if (pos >= 0) {
         ctl = claimed ? alloc_row(t) : s.ctl;
-        if (blacklist && blacklist[i]) {
+        // ids must be distinct; should a duplicate of this launch have claimed the key a moment
+        // ago, wait for it to publish - a row pointer is only ever derived from a READY ctl
+        for (int spin = 0; !claimed && !(ctl & CTL_READY) && spin < (1 << 14); ++spin)
+          ctl = ld_acquire_u32(&t.slots[pos].ctl);
+        if (!claimed && !(ctl & CTL_READY)) {
+          pos = -1;   // never published: skip the key rather than touch row 0
+        } else if (blacklist && blacklist[i]) {
           // TableManager::MarkBlacklistUnsafe, table_manager.h:335-357
           if (claimed) {
             t.slots[pos].freq = 1u << 16;
