@@ -408,15 +408,18 @@ class PeerShardedStep(PaddedShardedStep):
                                           self.seg_rows[0], C)
     main.wait_stream(s1)           # arriving at B also says: I am done reading my inbox
     self._barrier()                # B: my rows have arrived
-    if self.fused_route:           # every owner has read its inbox: pad it for the next step
-      ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
     ops.expand_rows(self.rows_in[0], self.route["perm"], self.idx, B, out)
     # ---- [the model runs here: `grad` is a function of `out`] ----
     ops.unsorted_segment_sum(grad, self.idx, self.num, out=self.gsum)
     # gradient exchange: the sums go to the owners' buffers
     ops.scatter_rows_n_peer(self.gsum, self.route["perm"], B, self.num, self.seg_grads[0], C)
     self._barrier()                # C: every peer's gradient sums have arrived
+    if self.fused_route:           # every owner has read its inbox (B): pad it for the next step,
+      with t.cuda.stream(s1):      # beside the owner update
+        s1.wait_stream(main)
+        ops.route_fill_peer(G, C, self.seg_ids[0], self.seg_occ[0], self.route["counts"])
     self._owner_update()
+    main.wait_stream(s1)
     return out
 
   def run_rotation(self, ids_list, grad_list, out=None):
@@ -424,13 +427,12 @@ class PeerShardedStep(PaddedShardedStep):
 
     The chain that must run step after step is  lookup(t) -> barrier B(t) -> expand(t) ->
     [model] -> local gradient sum(t) -> gradient exchange(t) -> barrier C(t) -> owner sum(t) ->
-    apply(t) -> lookup(t+1).  Fed to it from the side:
+    apply(t) -> lookup(t+1); all of it is issued on the calling stream.  Fed to it from the side:
       s_r  requester: dedup+route(t) [= id exchange], step after step;
       s_o  barrier A(t) (channel 0: every peer's ids(t) are in my inbox) and the owner-side
            dedup(t), which therefore run under step t-1;
       s_z  the zero-fill of the owner sums' destination;
-      s_e  after barrier B(t): pad the inbox for step t+2, expand the rows of step t, then the
-           local gradient sum and the gradient exchange of step t (they follow the expand).
+      s_e  after barrier B(t): pad the inbox for step t+2.
     Step t uses buffer set t % 2 of everything exchanged.  Who may overwrite what, and why it
     is safe, is argued hazard by hazard in DESIGN.md (section 6)."""
     assert len(ids_list) % 2 == 0 and self.fused_route
@@ -439,6 +441,8 @@ class PeerShardedStep(PaddedShardedStep):
     out = self.out if out is None else out
     main = t.cuda.current_stream(self.dev)
     s_r, s_o, s_e, s_z = self.side, self.side2, self.side3, self.side4
+    for S in self.sets:       # the local gradient sums accumulate into cleared buffers
+      ops.zero_rows(S["gsum"])
     for s in (s_r, s_o, s_e, s_z):
       s.wait_stream(main)
     ev_g = [None, None]       # expand + gradient exchange of the last step on buffer set p
@@ -477,16 +481,20 @@ class PeerShardedStep(PaddedShardedStep):
       self._barrier(1)             # B(t): my rows have arrived
       ev_b = t.cuda.Event()
       ev_b.record(main)
-      with t.cuda.stream(s_e):
-        s_e.wait_event(ev_b)
+      # the chain continues on this stream (a hop to another stream costs microseconds)
+      ops.expand_rows(self.rows_in[p], S["route"]["perm"], S["idx"], B, out)
+      # [the model runs here: `grad` is a function of `out`]
+      ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"], accumulate=True)
+      ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads[p], C)
+      ev_sc = t.cuda.Event()
+      ev_sc.record(main)           # set p's perm / idx / sums have been read
+      with t.cuda.stream(s_e):     # off the chain: every owner has read inbox p (they passed B):
+        s_e.wait_event(ev_b)       # pad it for step t+2 ...
         ops.route_fill_peer(G, C, self.seg_ids[p], self.seg_occ[p], S["route"]["counts"])
-        ops.expand_rows(self.rows_in[p], S["route"]["perm"], S["idx"], B, out)
-        # [the model runs here: `grad` is a function of `out`]
-        ops.unsorted_segment_sum(grad, S["idx"], S["num"], out=S["gsum"])
-        ops.scatter_rows_n_peer(S["gsum"], S["route"]["perm"], B, S["num"], self.seg_grads[p], C)
+        s_e.wait_event(ev_sc)      # ... and clear set p's sums for step t+2 (the sum accumulates)
+        ops.zero_rows(S["gsum"], S["num"])
         ev_g[p] = t.cuda.Event()
         ev_g[p].record(s_e)
-      main.wait_event(ev_g[p])     # my gradient sums are stored before I say so
       main.wait_event(ev_z)
       self._barrier(2)             # C(t): every peer's gradient sums have arrived
       self._owner_update(p)
