@@ -513,6 +513,7 @@ class LocalStepper:
     self.side = torch.cuda.Stream(device=dev, priority=0)
     self.chain = torch.cuda.Stream(device=dev, priority=-1 if prio else 0)
     self.lookahead = os.environ.get("KVHBM_BENCH_PLAN_AHEAD", "1") != "0"
+    self.prebuilt = os.environ.get("KVHBM_BENCH_PLAN_PREBUILT", "0") == "1"
 
   def populate(self):
     torch, ops = self.torch, self.ops
@@ -600,7 +601,8 @@ class LocalStepper:
       with torch.cuda.stream(side):
         if nxt == 0:
           side.wait_event(ev_apply[0])            # the last reader of plan(0)'s buffers
-        self.stage("unique", self.ids_d[nxt], None, self.plans[nxt], None)
+        if not self.prebuilt:                     # (diagnostic: the chain alone, plans left from warm-up)
+          self.stage("unique", self.ids_d[nxt], None, self.plans[nxt], None)
         ev_plan[nxt] = torch.cuda.Event()
         ev_plan[nxt].record(side)
     main.wait_stream(side)

@@ -396,6 +396,10 @@ struct GradSrc {
   // group of neighbours there would sum eight 30-row segments one after the other (measured:
   // 66 us for such a group, 17 us for a typical one), a strided group gets one of them at most
   long long stride = 1;
+  // planned groups: pull the rows of the group's later rounds (and the occurrences beyond the
+  // fourth) into L2 while the first round's loads are in flight - a later round then waits for
+  // an L2 hit instead of a DRAM round trip, and it costs no registers
+  bool prefetch = false;
 #ifdef KVHBM_TRACE
   unsigned long long* trace = nullptr;   // [16] timestamps of one group (tuning aid)
 #endif
@@ -588,6 +592,37 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
             } else chunk_zero(s[u][r][q]);
           }
         }
+        if (planned && gs.prefetch && it == 0 && u == 0) {
+          // later rounds of this tile: value + slot rows and the first four gradient rows (all
+          // addresses are in shared memory since phase 1)
+          for (int r2 = UNR; r2 < steps; ++r2) {
+            const int k2 = r2 * kpi + tq;
+            const int m2 = sm.modes[wib][k2];
+            const int v2m = (m2 & 0xff) - 1, a2m = ((m2 >> 8) & 0xff) - 1, b2m = ((m2 >> 16) & 0xff) - 1;
+            if (v2m == V_SKIP) continue;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              const int off = (q * tpr + tl) * VEC;
+              if (off >= dim) continue;
+              if (v2m == V_COPY || v2m == V_KEEP) prefetch_l2(sm.vp[wib][k2] + off);
+#pragma unroll
+              for (int r = 0; r < PARTS; ++r) {
+                const bool second = TWO && r == 1;
+                if ((second ? b2m : a2m) == V_COPY)
+                  prefetch_l2((second ? sm.bp[wib][k2] : sm.ap[wib][k2]) + (TWO ? 0 : r * dim) + off);
+              }
+            }
+            const int c2 = sm.gcnt[wib][k2] < 4 ? sm.gcnt[wib][k2] : 4;
+            for (int j = 0; j < c2; ++j) {
+              const float* gp = gs.grad + (long long)sm.gpos[wib][k2][j] * dim;
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) {
+                const int off = (q * tpr + tl) * VEC;
+                if (off < dim) prefetch_l2(gp + off);
+              }
+            }
+          }
+        }
         if (!planned) {
           const long long gi = base + kl - gs.row0;
           if (gs.ready && gi < n - gs.row0) {
@@ -622,6 +657,13 @@ __device__ __forceinline__ void apply_group(ApplySmem<NW, VEC, CPL>& sm, int wib
                   const int off = (q * tpr + tl) * VEC;
                   if (off < dim) t[j][q].load_stream(gp + off); else chunk_zero(t[j][q]);
                 }
+              }
+            }
+            if (gs.prefetch && k0 == 0 && cnt > GU) {
+              // an id with more occurrences: its remaining rows, one occurrence per lane of the tile
+              for (int k = GU + tl; k < cnt; k += tpr) {
+                const char* gp = reinterpret_cast<const char*>(gs.grad + (long long)__ldg(pl + k) * dim);
+                for (int b = 0; b < dim * 4; b += 128) prefetch_l2(gp + b);
               }
             }
 #pragma unroll

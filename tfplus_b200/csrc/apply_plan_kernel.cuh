@@ -296,6 +296,8 @@ apply_plan_kernel(const __grid_constant__ TableView var, const __grid_constant__
     GradSrc gs;
     gs.grad = grad; gs.row0 = 0; gs.counts = pl.counts; gs.seg_off = pl.seg_off; gs.pos = pl.pos;
     gs.heavy_t = pl.heavy_t; gs.hint = pl.hint; gs.cg = false;
+    gs.prefetch = (guided & 2) != 0;
+    guided &= 1;
     // Guided sizes: the first three quarters of the ranks go out in groups of `kpw` ids, the
     // last quarter in groups of one round (32 / tpr ids) - what is still unclaimed when the pool
     // runs dry costs the launch one group-time, so the last groups are the short ones.  Both
@@ -355,9 +357,19 @@ int launch_apply_plan(Table* var, Table* sa, Table* sb, const PlanView& pv, cons
                       const ApplyParams& p, const float* d_hp, uint16_t today, cudaStream_t st,
                       int tpr, float* d_adv) {
   static const int kpw_env = getenv("KVHBM_APPLYP_KPW") ? atoi(getenv("KVHBM_APPLYP_KPW")) : 0;
-  static const int guided_env = getenv("KVHBM_APPLYP_GUIDED") ? atoi(getenv("KVHBM_APPLYP_GUIDED")) : 1;
+  static const int guided_env = (getenv("KVHBM_APPLYP_GUIDED") ? atoi(getenv("KVHBM_APPLYP_GUIDED")) : 1) |
+                                ((getenv("KVHBM_APPLYP_PREFETCH") ? atoi(getenv("KVHBM_APPLYP_PREFETCH")) : 1) << 1);
   constexpr int bps_env = 1;
-  const int sms = sm_count(var->device);
+  // One persistent block fills an SM (96 registers x 640 threads), so a full grid starves
+  // whatever runs beside the step - the input pipeline's dedup plan of the next batch - until the
+  // launch drains, and the chain then waits for that plan: 81.9 us per step.  The launch is
+  // bound by the head id's chain and the light path's latency, not by SM count (47.6 us on 148
+  // SMs, 48.6 on 132), so one SM in nine is left free: 67.6 us per step with the plan beside
+  // it (64.1 with prebuilt plans).  KVHBM_APPLYP_SMS overrides.
+  static const int sms_env = getenv("KVHBM_APPLYP_SMS") ? atoi(getenv("KVHBM_APPLYP_SMS")) : 0;
+  int sms = sm_count(var->device);
+  if (sms >= 36) sms -= sms / 9;
+  if (sms_env > 0 && sms_env <= sm_count(var->device)) sms = sms_env;
   const int kpi = 32 / tpr;
   // light warps of a full grid; a Zipf batch has ~n/3 distinct ids
   // Light groups are latency chains: ~3 us of probes, then per round of 32 / tpr ids ~1.8 us for

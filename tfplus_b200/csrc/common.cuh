@@ -260,6 +260,11 @@ __host__ __device__ __forceinline__ uint32_t freq_day(uint32_t w) { return w & 0
 __host__ __device__ __forceinline__ uint32_t freq_to_ref(uint32_t w) { return (w << 16) | (w >> 16); }
 
 // ---- row tiles ----------------------------------------------------------------------
+// A hint only: pull the line holding `p` into L2 (no register, no wait).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // A row of `dim` floats is moved by a tile of `tpr` lanes (power of two <= 32),
 // each lane owning `CPL` chunks of VEC floats: chunk c of lane l covers floats
 // [(c * tpr + l) * VEC, +VEC).  VEC = 4 (128-bit) when dim % 4 == 0, else 1.
