@@ -1,8 +1,17 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 200 --warmup 20 > gpurun_out/r02_bench_n1.json 2> gpurun_out/n1.err || tail -5 gpurun_out/n1.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r02_bench_n1.json'))
-print('n1', round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], d['roofline']['frac'], d['cpu_baseline']['value'])
+run() { # name, env...
+  name=$1; shift
+  env "$@" python bench.py --steps 208 --warmup 16 --no-cpu --no-check > gpurun_out/exp_$name.json 2> gpurun_out/exp_$name.err || tail -3 gpurun_out/exp_$name.err
+  python - $name <<'PY'
+import json,sys
+d=json.load(open('gpurun_out/exp_%s.json'%sys.argv[1]))
+st=d['roofline']['stages']
+print(sys.argv[1], 'step', round(d['ms_per_step']*1e3,1), 'strict', round(d['strict_per_step']['ms_per_step']*1e3,1), {k:round(v['ms']*1e3,1) for k,v in st.items()})
 PY
+}
+run ring9
+run ring9_k8 KVHBM_APPLYP_KPW=8
+python -m pytest tests/test_gpu_plan.py -x -q -m gpu 2>&1 | tail -1
+cp tfplus_b200/build/libkvhbm_trace.so tfplus_b200/libkvhbm.so
+python scripts/trace_apply_plan.py > gpurun_out/trace_ring9.log 2>&1
+tail -12 gpurun_out/trace_ring9.log

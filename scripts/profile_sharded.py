@@ -12,7 +12,7 @@ dev = torch.device("cuda", rank)
 dist.init_process_group("nccl", device_id=dev)
 ops.set_today(bench.TODAY)
 keys = int(os.environ.get("KEYS", "2000000"))
-st = sharded.ShardedStepper(keys, bench.DIM, bench.BATCH, bench.HP, dev, rank, world)
+st = bench.ShardedStepper(keys, bench.DIM, bench.BATCH, bench.HP, dev, rank, world)
 st.populate()
 ids_np, g_np = bench.make_batches(4, keys * world, bench.BATCH, bench.DIM, seed_ids=2024 + rank, seed_grad=7 + rank)
 ids = [torch.from_numpy(x).to(dev) for x in ids_np]
