@@ -34,6 +34,16 @@ INIT_ROWS = 10000
 ZIPF_S = 1.1
 PERM_A = 7368787            # rank -> id: (rank * A) mod KEYS, A coprime to 10^7
 N_BATCHES = 16              # rotating input batches (16 x 17.3 MB = 277 MB > 126 MB L2)
+
+
+def pick_rotation(steps):
+  """Rotating batches for a K-step run: the largest even n in 8..16 that divides K, so that all K
+  timed steps are whole rotation graphs (8 x 17.3 MB = 138 MB is still more than the 126 MB L2);
+  16 when there is none (the remainder then runs as strict steps, and the line says so)."""
+  for n in range(16, 7, -2):
+    if steps >= n and steps % n == 0:
+      return n
+  return 16
 HP = dict(lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, l1=1e-5, l2=1e-5, l21=1e-5)
 TODAY = 20000
 METRIC = "KvVariable lookup+GroupAdam apply keys/s"
@@ -1077,6 +1087,8 @@ def main():
     bench_configs.bench._OUT = _OUT      # (this file runs as __main__: share the real stdout)
     bench_configs.RUNNERS[args.config](args)
     return 0
+  global N_BATCHES
+  N_BATCHES = pick_rotation(args.steps)
   return main_ours(args)
 
 

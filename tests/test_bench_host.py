@@ -78,3 +78,11 @@ def test_batches_are_deterministic_and_zipf_shaped():
   assert 19_000 < u < 23_000          # SURVEY: U ~ 20.3 K unique of 65 536 at Zipf(1.1)
   _, counts = np.unique(ids, return_counts=True)
   assert counts.max() > 5_000         # the head id takes ~10 % of the batch
+
+
+@pytest.mark.parametrize("K,n", [(20, 10), (200, 10), (208, 16), (16, 16), (30, 10), (24, 12),
+                                 (100, 10), (17, 16), (3, 16), (64, 16), (28, 14)])
+def test_rotation_length_divides_the_timed_steps(K, n):
+  # all K timed steps run as whole rotation graphs whenever an even n in 8..16 divides K
+  assert bench.pick_rotation(K) == n
+  assert n % 2 == 0 and 8 <= n <= 16
