@@ -1,10 +1,12 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 200 --warmup 20 > gpurun_out/r02_bench_n1.json 2> gpurun_out/n1.err || tail -5 gpurun_out/n1.err
-python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1_k20.json 2> gpurun_out/n1b.err || tail -5 gpurun_out/n1b.err
-python - <<'PY'
-import json
-for f in ('r02_bench_n1','r02_bench_n1_k20'):
-  d=json.load(open('gpurun_out/%s.json'%f))
-  print(f, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], d['roofline']['frac'], d['cpu_baseline']['value'], d['schedule'][-80:])
+N=${1:-2}
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"
+$T bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/n$N.err || tail -5 gpurun_out/n$N.err
+python - $N <<'PY'
+import json,sys
+N=sys.argv[1]
+d=json.load(open('gpurun_out/r02_bench_n%s.json'%N))
+print('n'+N, round(d['value']/1e9,3), round(d['ms_per_step']*1e3,1), round(d['strict_per_step']['ms_per_step']*1e3,1), round(d['e2e']['value']/1e6,1), d['parity_check']['ok'], d['nvlink']['bus_gbs_per_gpu'], d['schedule'][-80:])
 PY
-python -c "import __graft_entry__ as g; g.smoke()"
+
+
