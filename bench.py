@@ -241,6 +241,30 @@ def workload_config(args, n_gpus):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(torch, local_rank):
+  """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers
+  of the end-to-end leg are first-touched there and their PCIe traffic stays on that socket
+  (torchrun pins nothing; eight ranks' buffers on one node cost the 8-GPU e2e leg its scaling).
+  Returns a description for the JSON line, or None when the topology is not exposed."""
+  try:
+    pr = torch.cuda.get_device_properties(local_rank)
+    bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+    if node < 0:
+      return None
+    cpus = set()
+    for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+      lo, _, hi = part.partition("-")
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return None
+    os.sched_setaffinity(0, cpus)
+    return {"gpu": bdf, "numa_node": node, "cpus": len(cpus)}
+  except (OSError, ValueError, AttributeError, RuntimeError):
+    return None
+
+
 def main_ours(args):
   import torch
   import torch.distributed as dist
@@ -260,6 +284,9 @@ def main_ours(args):
                      "use --impl reference for the CPU arm")
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
+  # (N = 1 keeps every host core: the cpu_baseline leg runs in this process)
+  numa = bind_to_gpu_numa_node(torch, local_rank) if (
+      world > 1 and os.environ.get("KVHBM_BENCH_NUMA", "1") != "0") else None
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   ops.set_today(TODAY)
@@ -420,7 +447,8 @@ def main_ours(args):
         "strict_per_step": strict,
         "e2e": {"value": e2e_val, "unit": UNIT,
                 "h2d_bytes_per_step": int(B * 8 + B * D * 4),
-                "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K},
+                "d2h_bytes_per_step": int(B * D * 4), "ms_per_step": e2e_ms / K,
+                "host_numa_binding": numa},
         "roofline": roof,
         "parity_check": check,
     }
